@@ -1,0 +1,544 @@
+// fiss_abi.cu -- host side of libfissgpu.so: the C ABI declared in include/fiss_abi.h.
+//
+// Plain CUDA runtime; no torch, no Python.  A handle owns the uploaded scene tables, pinned host
+// staging and device scratch for the *_host entry points; the *_dev entry points only launch on
+// caller-owned buffers.  Every launch is a persistent grid sized from the SM count and the
+// kernel's occupancy for the shared-memory footprint of the current scene.
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "fiss_kernels.cuh"
+
+namespace {
+
+std::string g_create_error;
+
+struct DevBuf {
+  void* p = nullptr;
+  size_t cap = 0;
+  cudaError_t ensure(size_t bytes) {
+    if (bytes <= cap) return cudaSuccess;
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+    size_t want = std::max(bytes, (size_t)4096);
+    cudaError_t e = cudaMalloc(&p, want);
+    if (e == cudaSuccess) cap = want;
+    return e;
+  }
+  void release() {
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+  }
+  template <typename T>
+  T* as() const { return static_cast<T*>(p); }
+};
+
+struct PinBuf {
+  void* p = nullptr;
+  size_t cap = 0;
+  cudaError_t ensure(size_t bytes) {
+    if (bytes <= cap) return cudaSuccess;
+    if (p) cudaFreeHost(p);
+    p = nullptr;
+    cap = 0;
+    size_t want = std::max(bytes, (size_t)4096);
+    cudaError_t e = cudaHostAlloc(&p, want, cudaHostAllocDefault);
+    if (e == cudaSuccess) cap = want;
+    return e;
+  }
+  void release() {
+    if (p) cudaFreeHost(p);
+    p = nullptr;
+    cap = 0;
+  }
+  template <typename T>
+  T* as() const { return static_cast<T*>(p); }
+};
+
+constexpr size_t kSmemLimit = 227 * 1024;      // opt-in maximum per CTA on sm_100
+constexpr size_t kSmemObsBudget = 100 * 1024;  // stage obstacle rows only while 2 CTAs/SM still fit
+
+}  // namespace
+
+struct fiss_handle {
+  int device = 0;
+  int sm_count = 148;
+  std::string err;
+  int64_t launches = 0;
+  // scene
+  DevBuf spline;
+  int K = 0, Kp = 0;
+  DevBuf obs_tab, obs_const, obs_raw, obs_lw, obs_valid;
+  int M = 0, Mp = 0, mp_shift = 0, T_obs = 0, final_time_step = 0;
+  // *_host staging
+  DevBuf d_ego, d_end, d_cost, d_flags, d_best_idx, d_best_cost, d_meta, d_records, d_sel;
+  PinBuf h_in, h_out;
+  std::vector<double> end_cache;
+  size_t smem_attr[4] = {0, 0, 0, 0};
+};
+
+namespace {
+
+int32_t fail(fiss_handle* h, int32_t code, const std::string& msg) {
+  if (h) h->err = msg;
+  else g_create_error = msg;
+  return code;
+}
+
+#define FISS_CUDA(h, expr)                                                                        \
+  do {                                                                                            \
+    cudaError_t e_ = (expr);                                                                      \
+    if (e_ != cudaSuccess)                                                                        \
+      return fail(h, FISS_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(e_));          \
+  } while (0)
+
+int32_t check_params(fiss_handle* h, const fiss_params* p) {
+  if (!p) return fail(h, FISS_ERR_INVALID, "params is NULL");
+  if (!(p->tick_t > 0.0)) return fail(h, FISS_ERR_INVALID, "tick_t must be > 0");
+  if (p->check_res < 1) return fail(h, FISS_ERR_INVALID, "check_res must be >= 1");
+  if (p->time_step_now < 0) return fail(h, FISS_ERR_INVALID, "time_step_now must be >= 0");
+  return FISS_OK;
+}
+
+struct LaunchPlan {
+  fiss::EvalArgs a;
+  size_t smem = 0;
+  int grid = 1;
+  int threads = fiss::kThreads;
+};
+
+template <bool kMat, bool kRec>
+int32_t launch_eval(fiss_handle* h, cudaStream_t st, LaunchPlan& lp, int which) {
+  auto kern = fiss::fiss_eval_kernel<kMat, kRec>;
+  if (lp.smem > h->smem_attr[which]) {
+    FISS_CUDA(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemLimit));
+    h->smem_attr[which] = kSmemLimit;
+  }
+  int occ = 1;
+  FISS_CUDA(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, lp.threads, lp.smem));
+  occ = std::max(occ, 1);
+  const int warps = lp.threads / 32;
+  const int64_t need = (lp.a.total + warps - 1) / warps;
+  lp.grid = (int)std::max<int64_t>(1, std::min<int64_t>(need, (int64_t)h->sm_count * occ));
+  kern<<<lp.grid, lp.threads, lp.smem, st>>>(lp.a);
+  h->launches++;
+  FISS_CUDA(h, cudaGetLastError());
+  return FISS_OK;
+}
+
+// Fill everything of EvalArgs that depends on the scene and on the step bound `n_bound`.
+int32_t plan_launch(fiss_handle* h, const fiss_params* p, int64_t total, int n_bound, LaunchPlan& lp) {
+  if (h->K < 2) return fail(h, FISS_ERR_STATE, "fiss_set_spline has not been called");
+  if (n_bound < 1) return fail(h, FISS_ERR_INVALID, "n_stride must be >= the largest step count n (>= 1)");
+  fiss::EvalArgs& a = lp.a;
+  a.p = *p;
+  a.total = total;
+  a.spline = h->spline.as<double>();
+  a.K = h->K;
+  a.Kp = h->Kp;
+  int it = 0;
+  while ((1 << it) < std::max(h->K - 1, 1)) ++it;
+  a.search_iters = it;
+  a.obs_tab = h->obs_tab.as<double>();
+  a.obs_const = h->obs_const.as<double>();
+  a.M = h->M;
+  a.Mp = h->Mp;
+  a.mp_shift = h->mp_shift;
+  a.T_obs = h->T_obs;
+  a.final_time_step = h->final_time_step;
+  a.n_pad = (n_bound + 1) & ~1;
+  a.e_cap = (a.n_pad + p->check_res - 1) / p->check_res;
+  a.e_cap = (a.e_cap + 1) & ~1;
+  const int horizon = std::max(0, std::min(n_bound, h->final_time_step - p->time_step_now));
+  a.E_max = h->M > 0 ? (horizon + p->check_res - 1) / p->check_res : 0;
+  // few candidates: fewer warps per CTA so that the work spreads over more SMs (latency case, B = 1)
+  int warps = (int)std::min<int64_t>(fiss::kWarpsPerCta, std::max<int64_t>(1, (total + h->sm_count - 1) / h->sm_count));
+  lp.threads = warps * 32;
+  const size_t base = 16 + (size_t)9 * a.Kp * 8 + (size_t)4 * a.Mp * 8 +
+                      (size_t)warps * fiss::scratch_doubles_per_warp(a.n_pad, a.e_cap) * 8;
+  const size_t obs_bytes = (size_t)a.E_max * a.Mp * 32;
+  a.obs_in_smem = (a.E_max > 0 && base + obs_bytes <= kSmemObsBudget) ? 1 : 0;
+  if (!a.obs_in_smem) a.E_max = 0;
+  lp.smem = base + (a.obs_in_smem ? obs_bytes : 0);
+  if (lp.smem > kSmemLimit)
+    return fail(h, FISS_ERR_CAPACITY, "spline table + per-warp scratch exceed 227 KB of shared memory");
+  return FISS_OK;
+}
+
+int max_steps(const double* end, int C) {
+  int n = 0;
+  for (int c = 0; c < C; ++c) n = std::max(n, (int)end[4 * (size_t)c + 3]);
+  return n;
+}
+
+int32_t check_end_states(fiss_handle* h, const double* end, int C, int n_stride) {
+  for (int c = 0; c < C; ++c) {
+    const double T = end[4 * (size_t)c + 2], n = end[4 * (size_t)c + 3];
+    if (!(T > 0.0) || !(n >= 1.0) || n != std::floor(n))
+      return fail(h, FISS_ERR_INVALID, "end state " + std::to_string(c) + ": need T > 0 and an integral n >= 1");
+    if (n > n_stride) return fail(h, FISS_ERR_INVALID, "n_stride is smaller than a candidate's step count");
+  }
+  return FISS_OK;
+}
+
+}  // namespace
+
+// ================================================================================================
+extern "C" {
+
+int32_t fiss_abi_version(void) { return 1; }
+
+int32_t fiss_arange_len(double T, double tick) {
+  if (!(tick > 0.0) || !(T > 0.0)) return 0;
+  const double len = std::ceil((T - 0.0) / tick);  // NumPy: ceil((stop - start) / step) in double
+  if (!(len < 2147483647.0)) return -1;
+  return (int32_t)len;
+}
+
+int32_t fiss_create(int32_t device, fiss_handle** out) {
+  if (!out) return fail(nullptr, FISS_ERR_INVALID, "out is NULL");
+  *out = nullptr;
+  int count = 0;
+  cudaError_t e = cudaGetDeviceCount(&count);
+  if (e != cudaSuccess || count <= 0)
+    return fail(nullptr, FISS_ERR_CUDA,
+                std::string("no CUDA device: ") + (e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0"));
+  if (device < 0 || device >= count) return fail(nullptr, FISS_ERR_INVALID, "device index out of range");
+  e = cudaSetDevice(device);
+  if (e != cudaSuccess) return fail(nullptr, FISS_ERR_CUDA, std::string("cudaSetDevice: ") + cudaGetErrorString(e));
+  cudaDeviceProp prop;
+  e = cudaGetDeviceProperties(&prop, device);
+  if (e != cudaSuccess) return fail(nullptr, FISS_ERR_CUDA, std::string("cudaGetDeviceProperties: ") + cudaGetErrorString(e));
+  if (prop.major < 10)
+    return fail(nullptr, FISS_ERR_CUDA, "libfissgpu is built for sm_100a (Blackwell) only; found sm_" +
+                                            std::to_string(prop.major) + std::to_string(prop.minor));
+  fiss_handle* h = new (std::nothrow) fiss_handle();
+  if (!h) return fail(nullptr, FISS_ERR_CUDA, "out of host memory");
+  h->device = device;
+  h->sm_count = prop.multiProcessorCount;
+  *out = h;
+  return FISS_OK;
+}
+
+int32_t fiss_destroy(fiss_handle* h) {
+  if (!h) return FISS_OK;
+  cudaSetDevice(h->device);
+  for (DevBuf* b : {&h->spline, &h->obs_tab, &h->obs_const, &h->obs_raw, &h->obs_lw, &h->obs_valid, &h->d_ego,
+                    &h->d_end, &h->d_cost, &h->d_flags, &h->d_best_idx, &h->d_best_cost, &h->d_meta, &h->d_records,
+                    &h->d_sel})
+    b->release();
+  h->h_in.release();
+  h->h_out.release();
+  delete h;
+  return FISS_OK;
+}
+
+const char* fiss_last_error(const fiss_handle* h) { return h ? h->err.c_str() : g_create_error.c_str(); }
+
+int64_t fiss_launch_count(const fiss_handle* h) { return h ? h->launches : 0; }
+
+// ------------------------------------------------------------------------------------------------
+int32_t fiss_set_spline(fiss_handle* h, void* stream, const double* table, int32_t K) {
+  if (!h) return FISS_ERR_INVALID;
+  if (!table || K < 2) return fail(h, FISS_ERR_INVALID, "spline table needs K >= 2 knots");
+  cudaStream_t st = (cudaStream_t)stream;
+  FISS_CUDA(h, cudaSetDevice(h->device));
+  const int Kp = (K + 1) & ~1;  // even row length: every row is a multiple of 16 bytes for the bulk copy
+  for (int k = 1; k < K; ++k)
+    if (!(table[k] >= table[k - 1])) return fail(h, FISS_ERR_INVALID, "spline knots must be ascending");
+  FISS_CUDA(h, h->h_in.ensure((size_t)9 * Kp * 8));
+  double* stage = h->h_in.as<double>();
+  for (int r = 0; r < 9; ++r) {
+    std::memcpy(stage + (size_t)r * Kp, table + (size_t)r * K, (size_t)K * 8);
+    for (int k = K; k < Kp; ++k) stage[(size_t)r * Kp + k] = r == 0 ? INFINITY : 0.0;
+  }
+  FISS_CUDA(h, h->spline.ensure((size_t)9 * Kp * 8));
+  FISS_CUDA(h, cudaMemcpyAsync(h->spline.p, stage, (size_t)9 * Kp * 8, cudaMemcpyHostToDevice, st));
+  FISS_CUDA(h, cudaStreamSynchronize(st));
+  h->K = K;
+  h->Kp = Kp;
+  return FISS_OK;
+}
+
+static int32_t obstacle_dims(fiss_handle* h, int32_t M, int32_t T_obs, int32_t final_time_step) {
+  if (M < 0 || T_obs < 0) return fail(h, FISS_ERR_INVALID, "negative obstacle table size");
+  h->M = M;
+  h->T_obs = M > 0 ? T_obs : 0;
+  h->final_time_step = final_time_step;
+  if (M == 0) {
+    h->Mp = 0;
+    h->mp_shift = 0;
+    return FISS_OK;
+  }
+  if (M <= 32) {
+    int s = 0;
+    while ((1 << s) < M) ++s;
+    h->Mp = 1 << s;
+    h->mp_shift = s;
+  } else {
+    h->Mp = (M + 31) & ~31;
+    h->mp_shift = 5;
+  }
+  return FISS_OK;
+}
+
+int32_t fiss_set_obstacles(fiss_handle* h, void* stream, const double* xyth, const double* lw, const uint8_t* valid,
+                           int32_t M, int32_t T_obs, int32_t final_time_step) {
+  if (!h) return FISS_ERR_INVALID;
+  cudaStream_t st = (cudaStream_t)stream;
+  FISS_CUDA(h, cudaSetDevice(h->device));
+  if (M > 0 && (!xyth || !lw || !valid || T_obs < 1))
+    return fail(h, FISS_ERR_INVALID, "obstacle arrays are NULL or T_obs < 1");
+  int32_t rc = obstacle_dims(h, M, T_obs, final_time_step);
+  if (rc != FISS_OK || M == 0) return rc;
+  const size_t n_state = (size_t)M * T_obs;
+  FISS_CUDA(h, h->obs_raw.ensure(n_state * 3 * 8));
+  FISS_CUDA(h, h->obs_lw.ensure((size_t)M * 2 * 8));
+  FISS_CUDA(h, h->obs_valid.ensure(n_state));
+  FISS_CUDA(h, h->obs_tab.ensure((size_t)T_obs * h->Mp * 32));
+  FISS_CUDA(h, h->obs_const.ensure((size_t)h->Mp * 32));
+  FISS_CUDA(h, cudaMemcpyAsync(h->obs_raw.p, xyth, n_state * 3 * 8, cudaMemcpyHostToDevice, st));
+  FISS_CUDA(h, cudaMemcpyAsync(h->obs_lw.p, lw, (size_t)M * 2 * 8, cudaMemcpyHostToDevice, st));
+  FISS_CUDA(h, cudaMemcpyAsync(h->obs_valid.p, valid, n_state, cudaMemcpyHostToDevice, st));
+  const int64_t work = std::max<int64_t>((int64_t)T_obs * h->Mp, h->Mp);
+  fiss::fiss_obstacle_prep_kernel<<<(unsigned)((work + 255) / 256), 256, 0, st>>>(
+      h->obs_raw.as<double>(), h->obs_lw.as<double>(), h->obs_valid.as<uint8_t>(), M, h->Mp, T_obs,
+      h->obs_tab.as<double>(), h->obs_const.as<double>());
+  h->launches++;
+  FISS_CUDA(h, cudaGetLastError());
+  FISS_CUDA(h, cudaStreamSynchronize(st));  // the host arrays may be released by the caller on return
+  return FISS_OK;
+}
+
+int32_t fiss_set_obstacles_waymo(fiss_handle* h, void* stream, const float* trajs, const uint8_t* mask, int32_t N,
+                                 int32_t T, int32_t final_time_step) {
+  if (!h) return FISS_ERR_INVALID;
+  cudaStream_t st = (cudaStream_t)stream;
+  FISS_CUDA(h, cudaSetDevice(h->device));
+  if (N > 0 && (!trajs || !mask || T < 1)) return fail(h, FISS_ERR_INVALID, "waymo arrays are NULL or T < 1");
+  int32_t rc = obstacle_dims(h, N, T, final_time_step);
+  if (rc != FISS_OK || N == 0) return rc;
+  const size_t n_state = (size_t)N * T;
+  FISS_CUDA(h, h->obs_raw.ensure(n_state * 11 * 4));
+  FISS_CUDA(h, h->obs_valid.ensure(n_state));
+  FISS_CUDA(h, h->obs_tab.ensure((size_t)T * h->Mp * 32));
+  FISS_CUDA(h, h->obs_const.ensure((size_t)h->Mp * 32));
+  FISS_CUDA(h, cudaMemcpyAsync(h->obs_raw.p, trajs, n_state * 11 * 4, cudaMemcpyHostToDevice, st));
+  FISS_CUDA(h, cudaMemcpyAsync(h->obs_valid.p, mask, n_state, cudaMemcpyHostToDevice, st));
+  const int64_t work = std::max<int64_t>((int64_t)T * h->Mp, h->Mp);
+  fiss::fiss_obstacle_prep_waymo_kernel<<<(unsigned)((work + 255) / 256), 256, 0, st>>>(
+      h->obs_raw.as<float>(), h->obs_valid.as<uint8_t>(), N, h->Mp, T, h->obs_tab.as<double>(),
+      h->obs_const.as<double>());
+  h->launches++;
+  FISS_CUDA(h, cudaGetLastError());
+  FISS_CUDA(h, cudaStreamSynchronize(st));
+  return FISS_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+int32_t fiss_eval_candidates_dev(fiss_handle* h, void* stream, const double* d_ego, int32_t B, const double* d_end,
+                                 int32_t C, const fiss_params* p, double* d_cost, uint32_t* d_flags, double* d_mat,
+                                 int32_t n_stride) {
+  if (!h) return FISS_ERR_INVALID;
+  if (!d_ego || !d_end || B < 1 || C < 1) return fail(h, FISS_ERR_INVALID, "ego/end pointers or sizes invalid");
+  int32_t rc = check_params(h, p);
+  if (rc != FISS_OK) return rc;
+  FISS_CUDA(h, cudaSetDevice(h->device));
+  LaunchPlan lp{};
+  rc = plan_launch(h, p, (int64_t)B * C, n_stride, lp);
+  if (rc != FISS_OK) return rc;
+  lp.a.ego = d_ego;
+  lp.a.end = d_end;
+  lp.a.sel = nullptr;
+  lp.a.B = B;
+  lp.a.C = C;
+  lp.a.per_problem = 0;
+  lp.a.cost = d_cost;
+  lp.a.flags = d_flags;
+  lp.a.mat = d_mat;
+  lp.a.records = nullptr;
+  lp.a.n_stride = n_stride;
+  if (d_mat || p->check_curvature) return launch_eval<true, false>(h, (cudaStream_t)stream, lp, 1);
+  return launch_eval<false, false>(h, (cudaStream_t)stream, lp, 0);
+}
+
+int32_t fiss_full_records_dev(fiss_handle* h, void* stream, const double* d_ego6, const double* d_end,
+                              const int32_t* d_sel, int32_t N, const fiss_params* p, double* d_records,
+                              double* d_cost, uint32_t* d_flags, int32_t n_stride) {
+  if (!h) return FISS_ERR_INVALID;
+  if (!d_ego6 || !d_end || !d_records || N < 1) return fail(h, FISS_ERR_INVALID, "full_records: bad arguments");
+  int32_t rc = check_params(h, p);
+  if (rc != FISS_OK) return rc;
+  FISS_CUDA(h, cudaSetDevice(h->device));
+  LaunchPlan lp{};
+  rc = plan_launch(h, p, N, n_stride, lp);
+  if (rc != FISS_OK) return rc;
+  lp.a.ego = d_ego6;
+  lp.a.end = d_end;
+  lp.a.sel = d_sel;
+  lp.a.B = 1;
+  lp.a.C = N;
+  lp.a.per_problem = 0;
+  lp.a.cost = d_cost;
+  lp.a.flags = d_flags;
+  lp.a.mat = nullptr;
+  lp.a.records = d_records;
+  lp.a.n_stride = n_stride;
+  return launch_eval<false, true>(h, (cudaStream_t)stream, lp, 2);
+}
+
+int32_t fiss_pick_winners_dev(fiss_handle* h, void* stream, const double* d_ego, int32_t B, const double* d_end,
+                              int32_t C, const fiss_params* p, const double* d_cost, const uint32_t* d_flags,
+                              int32_t* d_best_idx, double* d_best_cost, double* d_records, int32_t* d_best_meta,
+                              int32_t n_stride) {
+  if (!h) return FISS_ERR_INVALID;
+  if (!d_ego || !d_end || !d_cost || !d_flags || !d_best_idx || !d_best_cost || B < 1 || C < 1)
+    return fail(h, FISS_ERR_INVALID, "pick_winners: bad arguments");
+  int32_t rc = check_params(h, p);
+  if (rc != FISS_OK) return rc;
+  FISS_CUDA(h, cudaSetDevice(h->device));
+  cudaStream_t st = (cudaStream_t)stream;
+  fiss::fiss_pick_kernel<<<B, fiss::kPickThreads, 0, st>>>(d_cost, d_flags, C, d_best_idx, d_best_cost);
+  h->launches++;
+  FISS_CUDA(h, cudaGetLastError());
+  if (d_best_meta) {
+    fiss::fiss_meta_kernel<<<(B + 127) / 128, 128, 0, st>>>(d_best_idx, d_end, d_flags, B, C, d_best_meta);
+    h->launches++;
+    FISS_CUDA(h, cudaGetLastError());
+  }
+  if (d_records) {
+    LaunchPlan lp{};
+    rc = plan_launch(h, p, B, n_stride, lp);
+    if (rc != FISS_OK) return rc;
+    lp.a.ego = d_ego;
+    lp.a.end = d_end;
+    lp.a.sel = d_best_idx;
+    lp.a.B = B;
+    lp.a.C = C;
+    lp.a.per_problem = 1;
+    lp.a.cost = nullptr;
+    lp.a.flags = nullptr;
+    lp.a.mat = nullptr;
+    lp.a.records = d_records;
+    lp.a.n_stride = n_stride;
+    return launch_eval<false, true>(h, st, lp, 2);
+  }
+  return FISS_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+static int32_t upload_end_states(fiss_handle* h, cudaStream_t st, const double* end, int32_t C) {
+  const size_t bytes = (size_t)C * 4 * 8;
+  if (h->end_cache.size() == (size_t)C * 4 && std::memcmp(h->end_cache.data(), end, bytes) == 0) return FISS_OK;
+  FISS_CUDA(h, h->d_end.ensure(bytes));
+  h->end_cache.assign(end, end + (size_t)C * 4);
+  // the cache vector is pageable memory: the copy is synchronous w.r.t. the host buffer, ordered on `st`
+  FISS_CUDA(h, cudaMemcpyAsync(h->d_end.p, h->end_cache.data(), bytes, cudaMemcpyHostToDevice, st));
+  return FISS_OK;
+}
+
+int32_t fiss_plan_lattice_host(fiss_handle* h, void* stream, const double* ego, int32_t B, const double* end,
+                               int32_t C, const fiss_params* p, int32_t* best_idx, double* best_cost,
+                               int32_t* best_meta, double* records, int32_t n_stride, double* cost, uint32_t* flags) {
+  if (!h) return FISS_ERR_INVALID;
+  if (!ego || !end || !best_idx || !best_cost || B < 1 || C < 1)
+    return fail(h, FISS_ERR_INVALID, "plan_lattice: bad arguments");
+  int32_t rc = check_params(h, p);
+  if (rc != FISS_OK) return rc;
+  rc = check_end_states(h, end, C, n_stride);
+  if (rc != FISS_OK) return rc;
+  FISS_CUDA(h, cudaSetDevice(h->device));
+  cudaStream_t st = (cudaStream_t)stream;
+  const size_t total = (size_t)B * C;
+  const size_t rec_doubles = records ? (size_t)B * FISS_REC_ROWS * n_stride : 0;
+  FISS_CUDA(h, h->d_ego.ensure((size_t)B * 48));
+  FISS_CUDA(h, h->d_cost.ensure(total * 8));
+  FISS_CUDA(h, h->d_flags.ensure(total * 4));
+  FISS_CUDA(h, h->d_best_idx.ensure((size_t)B * 4));
+  FISS_CUDA(h, h->d_best_cost.ensure((size_t)B * 8));
+  FISS_CUDA(h, h->d_meta.ensure((size_t)B * 8));
+  if (records) FISS_CUDA(h, h->d_records.ensure(rec_doubles * 8));
+  // pinned staging: [ego] in, [best_cost | records | cost | best_idx | meta | flags] out
+  FISS_CUDA(h, h->h_in.ensure((size_t)B * 48));
+  const size_t o_cost = 0, o_rec = o_cost + (size_t)B * 8, o_vol = o_rec + rec_doubles * 8,
+               o_idx = o_vol + (cost ? total * 8 : 0), o_meta = o_idx + (size_t)B * 4,
+               o_flags = o_meta + (size_t)B * 8, o_end = o_flags + (flags ? total * 4 : 0);
+  FISS_CUDA(h, h->h_out.ensure(o_end));
+  char* ho = h->h_out.as<char>();
+  std::memcpy(h->h_in.p, ego, (size_t)B * 48);
+  FISS_CUDA(h, cudaMemcpyAsync(h->d_ego.p, h->h_in.p, (size_t)B * 48, cudaMemcpyHostToDevice, st));
+  rc = upload_end_states(h, st, end, C);
+  if (rc != FISS_OK) return rc;
+  rc = fiss_eval_candidates_dev(h, stream, h->d_ego.as<double>(), B, h->d_end.as<double>(), C, p,
+                                h->d_cost.as<double>(), h->d_flags.as<uint32_t>(), nullptr, n_stride);
+  if (rc != FISS_OK) return rc;
+  rc = fiss_pick_winners_dev(h, stream, h->d_ego.as<double>(), B, h->d_end.as<double>(), C, p,
+                             h->d_cost.as<double>(), h->d_flags.as<uint32_t>(), h->d_best_idx.as<int32_t>(),
+                             h->d_best_cost.as<double>(), records ? h->d_records.as<double>() : nullptr,
+                             h->d_meta.as<int32_t>(), n_stride);
+  if (rc != FISS_OK) return rc;
+  FISS_CUDA(h, cudaMemcpyAsync(ho + o_cost, h->d_best_cost.p, (size_t)B * 8, cudaMemcpyDeviceToHost, st));
+  FISS_CUDA(h, cudaMemcpyAsync(ho + o_idx, h->d_best_idx.p, (size_t)B * 4, cudaMemcpyDeviceToHost, st));
+  FISS_CUDA(h, cudaMemcpyAsync(ho + o_meta, h->d_meta.p, (size_t)B * 8, cudaMemcpyDeviceToHost, st));
+  if (records) FISS_CUDA(h, cudaMemcpyAsync(ho + o_rec, h->d_records.p, rec_doubles * 8, cudaMemcpyDeviceToHost, st));
+  if (cost) FISS_CUDA(h, cudaMemcpyAsync(ho + o_vol, h->d_cost.p, total * 8, cudaMemcpyDeviceToHost, st));
+  if (flags) FISS_CUDA(h, cudaMemcpyAsync(ho + o_flags, h->d_flags.p, total * 4, cudaMemcpyDeviceToHost, st));
+  FISS_CUDA(h, cudaStreamSynchronize(st));
+  std::memcpy(best_cost, ho + o_cost, (size_t)B * 8);
+  std::memcpy(best_idx, ho + o_idx, (size_t)B * 4);
+  if (best_meta) std::memcpy(best_meta, ho + o_meta, (size_t)B * 8);
+  if (records) std::memcpy(records, ho + o_rec, rec_doubles * 8);
+  if (cost) std::memcpy(cost, ho + o_vol, total * 8);
+  if (flags) std::memcpy(flags, ho + o_flags, total * 4);
+  return FISS_OK;
+}
+
+int32_t fiss_eval_end_states_host(fiss_handle* h, void* stream, const double* ego6, const double* end, int32_t N,
+                                  const fiss_params* p, double* cost, uint32_t* flags, double* records,
+                                  int32_t n_stride) {
+  if (!h) return FISS_ERR_INVALID;
+  if (!ego6 || !end || !cost || !flags || N < 1) return fail(h, FISS_ERR_INVALID, "eval_end_states: bad arguments");
+  int32_t rc = check_params(h, p);
+  if (rc != FISS_OK) return rc;
+  rc = check_end_states(h, end, N, n_stride);
+  if (rc != FISS_OK) return rc;
+  FISS_CUDA(h, cudaSetDevice(h->device));
+  cudaStream_t st = (cudaStream_t)stream;
+  const size_t rec_doubles = records ? (size_t)N * FISS_REC_ROWS * n_stride : 0;
+  FISS_CUDA(h, h->d_ego.ensure(48));
+  FISS_CUDA(h, h->d_cost.ensure((size_t)N * 8));
+  FISS_CUDA(h, h->d_flags.ensure((size_t)N * 4));
+  if (records) FISS_CUDA(h, h->d_records.ensure(rec_doubles * 8));
+  FISS_CUDA(h, h->h_in.ensure(48));
+  const size_t o_cost = 0, o_rec = (size_t)N * 8, o_flags = o_rec + rec_doubles * 8, o_end = o_flags + (size_t)N * 4;
+  FISS_CUDA(h, h->h_out.ensure(o_end));
+  char* ho = h->h_out.as<char>();
+  std::memcpy(h->h_in.p, ego6, 48);
+  FISS_CUDA(h, cudaMemcpyAsync(h->d_ego.p, h->h_in.p, 48, cudaMemcpyHostToDevice, st));
+  rc = upload_end_states(h, st, end, N);
+  if (rc != FISS_OK) return rc;
+  if (records) {
+    rc = fiss_full_records_dev(h, stream, h->d_ego.as<double>(), h->d_end.as<double>(), nullptr, N, p,
+                               h->d_records.as<double>(), h->d_cost.as<double>(), h->d_flags.as<uint32_t>(), n_stride);
+  } else {
+    rc = fiss_eval_candidates_dev(h, stream, h->d_ego.as<double>(), 1, h->d_end.as<double>(), N, p,
+                                  h->d_cost.as<double>(), h->d_flags.as<uint32_t>(), nullptr, n_stride);
+  }
+  if (rc != FISS_OK) return rc;
+  FISS_CUDA(h, cudaMemcpyAsync(ho + o_cost, h->d_cost.p, (size_t)N * 8, cudaMemcpyDeviceToHost, st));
+  FISS_CUDA(h, cudaMemcpyAsync(ho + o_flags, h->d_flags.p, (size_t)N * 4, cudaMemcpyDeviceToHost, st));
+  if (records) FISS_CUDA(h, cudaMemcpyAsync(ho + o_rec, h->d_records.p, rec_doubles * 8, cudaMemcpyDeviceToHost, st));
+  FISS_CUDA(h, cudaStreamSynchronize(st));
+  std::memcpy(cost, ho + o_cost, (size_t)N * 8);
+  std::memcpy(flags, ho + o_flags, (size_t)N * 4);
+  if (records) std::memcpy(records, ho + o_rec, rec_doubles * 8);
+  return FISS_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,183 @@
+"""``FissEngine``: thin Python owner of one ``fiss_handle`` (one GPU, one stream).
+
+Host-side marshalling only: NumPy arrays in, NumPy arrays out; the arithmetic is in
+csrc/fiss_kernels.cuh.  The planners (``planners/*.py``) and the batched / multi-GPU front end
+(``batch.py``) sit on top of this class.  Device-pointer methods take torch tensors used purely as
+device buffers (``.data_ptr()``).
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from fiss_plus_planner_b200 import _shim
+from fiss_plus_planner_b200._shim import FissError, FissParams
+
+
+def end_state_table(d, v, T, tick: float) -> np.ndarray:
+    """``[C, 4] = (d_end, v_end, T, n)`` with ``n = len(np.arange(0, T, tick))``."""
+    d, v, T = np.broadcast_arrays(np.asarray(d, np.float64), np.asarray(v, np.float64), np.asarray(T, np.float64))
+    n = np.array([_shim.arange_len(t, tick) for t in T.ravel()], dtype=np.float64)
+    return np.ascontiguousarray(np.column_stack((d.ravel(), v.ravel(), T.ravel(), n)))
+
+
+def fop_lattice(settings, vehicle_w: float) -> np.ndarray:
+    """End states in FrenetOptimalPlanner.calc_frenet_paths order: d outer, T middle, v inner
+    (frenet_optimal_planner.py:72-78,89)."""
+    sw = settings.max_road_width - vehicle_w
+    ds = np.linspace(-sw / 2, sw / 2, settings.num_width)
+    Ts = np.linspace(settings.min_t, settings.max_t, settings.num_t)
+    vs = np.linspace(settings.lowest_speed, settings.highest_speed, settings.num_speed)
+    dd, TT, vv = np.meshgrid(ds, Ts, vs, indexing="ij")
+    return end_state_table(dd, vv, TT, settings.tick_t)
+
+
+def fiss_lattice(settings, vehicle_w: float):
+    """FISS grid ``[i_d][j_v][k_t]`` (fiss_planner.py:40-70): returns (table [C,4] in i,j,k order,
+    d samples, v samples, t samples, resolutions[3])."""
+    sw = settings.max_road_width - vehicle_w + 0.3
+    ds, rd = np.linspace(-sw / 2, sw / 2, settings.num_width, retstep=True)
+    vs, rv = np.linspace(settings.lowest_speed, settings.highest_speed, settings.num_speed, retstep=True)
+    ts, rt = np.linspace(settings.min_t, settings.max_t, settings.num_t, retstep=True)
+    dd, vv, tt = np.meshgrid(ds, vs, ts, indexing="ij")
+    return end_state_table(dd, vv, tt, settings.tick_t), ds, vs, ts, np.array([rd, rv, rt])
+
+
+def make_params(settings, vehicle, weights: dict, time_step_now: int = 0, check_res: int = 2,
+                check_curvature: bool = False, collide_all: bool = False) -> FissParams:
+    return FissParams(
+        tick_t=settings.tick_t, target_speed=settings.highest_speed, max_speed=vehicle.max_speed,
+        max_accel=vehicle.max_accel, max_curvature=float(getattr(vehicle, "max_curvature", np.inf)),
+        ego_length=vehicle.l, ego_width=vehicle.w, cost_time_offset=weights["time_offset"],
+        w_speed=weights["w_V"], w_accel=weights["w_A"], w_jerk=weights["w_J"], w_offset=weights["w_LC"],
+        time_step_now=int(time_step_now), check_res=int(check_res), check_curvature=int(check_curvature),
+        collide_all=int(collide_all))
+
+
+def decode_flags(flags: np.ndarray):
+    """flags word -> (constraint_ok, collision, n_cart)."""
+    flags = np.asarray(flags)
+    constraint_ok = (flags & (_shim.FLAG_SPEED | _shim.FLAG_ACCEL | _shim.FLAG_CURVATURE)) == 0
+    collision = (flags & _shim.FLAG_COLLISION) != 0
+    n_cart = (flags >> _shim.FLAG_NCART_SHIFT) & _shim.FLAG_NCART_MASK
+    return constraint_ok, collision, n_cart.astype(np.int64)
+
+
+class FissEngine:
+    def __init__(self, device: int = 0):
+        self._lib = _shim.load()
+        self._h = C.c_void_p()
+        rc = self._lib.fiss_create(int(device), C.byref(self._h))
+        if rc != _shim.FISS_OK:
+            raise FissError(f"fiss_create failed ({rc}): {self._lib.fiss_last_error(None).decode()}")
+        self.device = int(device)
+        self.num_obstacles = 0
+        self._obstacle_token = None
+
+    # ------------------------------------------------------------------ plumbing
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h.value:
+            self._lib.fiss_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc: int, what: str):
+        if rc != _shim.FISS_OK:
+            raise FissError(f"{what} failed ({rc}): {self._lib.fiss_last_error(self._h).decode()}")
+
+    @property
+    def launch_count(self) -> int:
+        return int(self._lib.fiss_launch_count(self._h))
+
+    @staticmethod
+    def _stream(stream):
+        return C.c_void_p(int(stream) if stream else 0)
+
+    # ------------------------------------------------------------------ scene tables
+    def set_spline(self, table: np.ndarray, stream=None):
+        table = np.ascontiguousarray(table, dtype=np.float64)
+        assert table.ndim == 2 and table.shape[0] == 9, "spline table must be [9, K]"
+        self._check(self._lib.fiss_set_spline(self._h, self._stream(stream), _shim.ptr(table), table.shape[1]),
+                    "fiss_set_spline")
+
+    def set_obstacles(self, xyth, lw, valid, final_time_step: int, stream=None):
+        if xyth is None or len(lw) == 0:
+            self._check(self._lib.fiss_set_obstacles(self._h, self._stream(stream), None, None, None, 0, 0,
+                                                     int(final_time_step)), "fiss_set_obstacles")
+            self.num_obstacles = 0
+            return
+        xyth = np.ascontiguousarray(xyth, dtype=np.float64)
+        lw = np.ascontiguousarray(lw, dtype=np.float64)
+        valid = np.ascontiguousarray(valid, dtype=np.uint8)
+        m, t = valid.shape
+        assert xyth.shape == (m, t, 3) and lw.shape == (m, 2)
+        self._check(self._lib.fiss_set_obstacles(self._h, self._stream(stream), _shim.ptr(xyth), _shim.ptr(lw),
+                                                 _shim.ptr(valid), m, t, int(final_time_step)), "fiss_set_obstacles")
+        self.num_obstacles = m
+
+    def set_obstacles_waymo(self, trajs, mask, final_time_step: int, stream=None):
+        trajs = np.ascontiguousarray(trajs, dtype=np.float32)
+        mask = np.ascontiguousarray(mask, dtype=np.uint8)
+        n, t, f = trajs.shape
+        assert f == 11 and mask.shape == (n, t)
+        self._check(self._lib.fiss_set_obstacles_waymo(self._h, self._stream(stream), _shim.ptr(trajs), _shim.ptr(mask),
+                                                       n, t, int(final_time_step)), "fiss_set_obstacles_waymo")
+        self.num_obstacles = n
+
+    # ------------------------------------------------------------------ host-pointer calls
+    def plan_lattice(self, ego: np.ndarray, end: np.ndarray, params: FissParams, want_records: bool = True,
+                     want_volume: bool = False, stream=None) -> dict:
+        """plan() for ``ego [B, 6]`` over the shared end-state table ``end [C, 4]``."""
+        ego = np.ascontiguousarray(np.atleast_2d(ego), dtype=np.float64)
+        end = np.ascontiguousarray(end, dtype=np.float64)
+        b, c = ego.shape[0], end.shape[0]
+        n_stride = int(end[:, 3].max())
+        best_idx = np.empty(b, np.int32)
+        best_cost = np.empty(b, np.float64)
+        meta = np.empty((b, 2), np.int32)
+        records = np.empty((b, _shim.REC_ROWS, n_stride), np.float64) if want_records else None
+        cost = np.empty((b, c), np.float64) if want_volume else None
+        flags = np.empty((b, c), np.uint32) if want_volume else None
+        self._check(self._lib.fiss_plan_lattice_host(
+            self._h, self._stream(stream), _shim.ptr(ego), b, _shim.ptr(end), c, C.byref(params), _shim.ptr(best_idx),
+            _shim.ptr(best_cost), _shim.ptr(meta), _shim.ptr(records), n_stride, _shim.ptr(cost), _shim.ptr(flags)),
+            "fiss_plan_lattice_host")
+        return dict(best_idx=best_idx, best_cost=best_cost, meta=meta, records=records, cost=cost, flags=flags)
+
+    def eval_end_states(self, ego6: np.ndarray, end: np.ndarray, params: FissParams, want_records: bool = False,
+                        stream=None) -> dict:
+        ego6 = np.ascontiguousarray(ego6, dtype=np.float64).reshape(6)
+        end = np.ascontiguousarray(end, dtype=np.float64)
+        n_end = end.shape[0]
+        n_stride = int(end[:, 3].max())
+        cost = np.empty(n_end, np.float64)
+        flags = np.empty(n_end, np.uint32)
+        records = np.empty((n_end, _shim.REC_ROWS, n_stride), np.float64) if want_records else None
+        self._check(self._lib.fiss_eval_end_states_host(
+            self._h, self._stream(stream), _shim.ptr(ego6), _shim.ptr(end), n_end, C.byref(params), _shim.ptr(cost),
+            _shim.ptr(flags), _shim.ptr(records), n_stride), "fiss_eval_end_states_host")
+        return dict(cost=cost, flags=flags, records=records)
+
+    # ------------------------------------------------------------------ device-pointer calls (torch tensors as buffers)
+    def eval_candidates_dev(self, ego_t, end_t, params: FissParams, cost_t, flags_t, mat_t, n_stride: int, stream=None):
+        b, c = ego_t.shape[0], end_t.shape[0]
+        self._check(self._lib.fiss_eval_candidates_dev(
+            self._h, self._stream(stream), C.c_void_p(ego_t.data_ptr()), b, C.c_void_p(end_t.data_ptr()), c,
+            C.byref(params), C.c_void_p(cost_t.data_ptr()), C.c_void_p(flags_t.data_ptr()),
+            C.c_void_p(mat_t.data_ptr()) if mat_t is not None else None, int(n_stride)), "fiss_eval_candidates_dev")
+
+    def pick_winners_dev(self, ego_t, end_t, params: FissParams, cost_t, flags_t, best_idx_t, best_cost_t,
+                         records_t, meta_t, n_stride: int, stream=None):
+        b, c = ego_t.shape[0], end_t.shape[0]
+        self._check(self._lib.fiss_pick_winners_dev(
+            self._h, self._stream(stream), C.c_void_p(ego_t.data_ptr()), b, C.c_void_p(end_t.data_ptr()), c,
+            C.byref(params), C.c_void_p(cost_t.data_ptr()), C.c_void_p(flags_t.data_ptr()),
+            C.c_void_p(best_idx_t.data_ptr()), C.c_void_p(best_cost_t.data_ptr()),
+            C.c_void_p(records_t.data_ptr()) if records_t is not None else None,
+            C.c_void_p(meta_t.data_ptr()) if meta_t is not None else None, int(n_stride)), "fiss_pick_winners_dev")

@@ -1,0 +1,247 @@
+"""FrenetOptimalPlanner on the B200 lattice engine -- drop-in for the reference class.
+
+Reference: planners/frenet_optimal_planner.py (``Stats`` :15-36, ``FrenetOptimalPlannerSettings``
+:38-56, ``FrenetOptimalPlanner`` :58-278).  Same constructor, attributes (``settings, vehicle,
+cubic_spline, best_traj, all_trajs, stats``) and methods (``generate_frenet_frame``, ``plan``).
+
+What differs is where the work happens.  The reference walks the (d, T, v) lattice in three nested
+Python loops and then runs calc_global_paths / check_constraints / check_collisions over Python
+lists.  Here ``plan()`` marshals six ego numbers, the end-state table and one ``fiss_params``
+struct, and ONE call into libfissgpu.so evaluates every candidate (one warp each), picks the
+winner with the reference's tie rule and returns the winner's arrays.  ``all_trajs`` stays
+populated (the GIF renderer reads it, planning.py:352-355) but lazily: a cycle's candidate bundle
+is only materialised on the device and copied back when somebody indexes it.
+"""
+from __future__ import annotations
+
+import collections.abc
+
+import numpy as np
+
+from fiss_plus_planner_b200 import _shim
+from fiss_plus_planner_b200.engine import FissEngine, decode_flags, fop_lattice, make_params
+from fiss_plus_planner_b200.planners.common.cost.cost_function import CostFunction
+from fiss_plus_planner_b200.planners.common.geometry.cubic_spline import CubicSpline2D
+from fiss_plus_planner_b200.planners.common.scenario.frenet import FrenetState, FrenetTrajectory
+from fiss_plus_planner_b200.planners.common.vehicle.vehicle import Vehicle
+
+
+class Stats(object):
+    def __init__(self):
+        self.num_iter = 0
+        self.num_trajs_generated = 0
+        self.num_trajs_validated = 0
+        self.num_collison_checks = 0
+
+    def __add__(self, other):
+        # accumulates in place and returns self, like the reference (:23-29)
+        self.num_iter += other.num_iter
+        self.num_trajs_generated += other.num_trajs_generated
+        self.num_trajs_validated += other.num_trajs_validated
+        self.num_collison_checks += other.num_collison_checks
+        return self
+
+    def average(self, value: int):
+        self.num_iter /= value
+        self.num_trajs_generated /= value
+        self.num_trajs_validated /= value
+        self.num_collison_checks /= value
+        return self
+
+
+class FrenetOptimalPlannerSettings(object):
+    def __init__(self, num_width: int = 5, num_speed: int = 5, num_t: int = 5):
+        self.tick_t = 0.1
+        self.max_road_width = 3.5
+        self.num_width = num_width
+        self.highest_speed = 13.4112
+        self.lowest_speed = 0.0
+        self.num_speed = num_speed
+        self.min_t = 8.0
+        self.max_t = 10.0
+        self.num_t = num_t
+        self.check_obstacle = True   # declared, never read -- as in the reference (:54-55)
+        self.check_boundary = True
+
+
+# ------------------------------------------------------------------------------------------------
+class ObstacleTable(object):
+    """Dense device-ready obstacle predictions (the wire format of ``fiss_set_obstacles``)."""
+
+    def __init__(self, xyth, lw, valid, final_time_step):
+        self.xyth = np.ascontiguousarray(xyth, dtype=np.float64)
+        self.lw = np.ascontiguousarray(lw, dtype=np.float64)
+        self.valid = np.ascontiguousarray(valid, dtype=np.uint8)
+        self.final_time_step = int(final_time_step)
+
+    def __len__(self):
+        return len(self.lw)
+
+
+def _rectangle_size(shape):
+    """(length, width) of a CommonRoad ``Rectangle``-like shape; falls back to the extent of its
+    ``shapely_object`` ring about the origin (the only thing the reference reads, :189)."""
+    if hasattr(shape, "length") and hasattr(shape, "width"):
+        return float(shape.length), float(shape.width)
+    ring = getattr(shape, "shapely_object", None)
+    if ring is not None:
+        pts = np.asarray(getattr(ring, "pts", None) if hasattr(ring, "pts") else ring.exterior.coords)
+        return float(pts[:, 0].max() - pts[:, 0].min()), float(pts[:, 1].max() - pts[:, 1].min())
+    raise TypeError("obstacle_shape must be a rectangle (length/width or shapely_object)")
+
+
+def marshal_obstacles(obstacles) -> ObstacleTable:
+    """CommonRoad-style obstacle objects -> dense table.  Reads exactly what has_collision reads
+    (:173,185-189): ``obstacles[0].prediction.final_time_step``, ``state_at_time(t)`` (None = absent)
+    with ``.position`` / ``.orientation``, and the rectangle size."""
+    if isinstance(obstacles, ObstacleTable):
+        return obstacles
+    if hasattr(obstacles, "xyth") and hasattr(obstacles, "lw"):     # synthetic.ObstacleSet
+        return ObstacleTable(obstacles.xyth, obstacles.lw, obstacles.valid, obstacles.final_time_step)
+    m = len(obstacles)
+    if m == 0:
+        return ObstacleTable(np.zeros((0, 0, 3)), np.zeros((0, 2)), np.zeros((0, 0)), 0)
+    final = int(obstacles[0].prediction.final_time_step)
+    horizon = final
+    for ob in obstacles:
+        pred = getattr(ob, "prediction", None)
+        if pred is not None and getattr(pred, "final_time_step", None) is not None:
+            horizon = max(horizon, int(pred.final_time_step))
+    t_obs = horizon + 1
+    xyth = np.zeros((m, t_obs, 3))
+    valid = np.zeros((m, t_obs), dtype=np.uint8)
+    lw = np.zeros((m, 2))
+    for j, ob in enumerate(obstacles):
+        lw[j] = _rectangle_size(ob.obstacle_shape)
+        for t in range(t_obs):
+            st = ob.state_at_time(t)
+            if st is not None:
+                xyth[j, t] = (st.position[0], st.position[1], st.orientation)
+                valid[j, t] = 1
+    return ObstacleTable(xyth, lw, valid, final)
+
+
+class CandidateBundle(collections.abc.Sequence):
+    """One cycle's candidates as a lazy sequence of ``FrenetTrajectory``.
+
+    Costs and masks are already on the host; the per-step arrays are produced by one
+    ``fiss_eval_end_states_host`` call (full records) the first time an element is touched."""
+
+    def __init__(self, engine: FissEngine, ego6, end, params, cost, flags, idx3=None):
+        self._engine, self._ego6, self._end, self._params = engine, np.array(ego6), np.array(end), params
+        self.cost = np.array(cost)
+        self.flags = np.array(flags)
+        self._idx3 = idx3
+        self._items = None
+
+    def __len__(self):
+        return len(self.cost)
+
+    def _materialize(self):
+        if self._items is None:
+            out = self._engine.eval_end_states(self._ego6, self._end, self._params, want_records=True)
+            _, _, n_cart = decode_flags(out["flags"])
+            items = []
+            for c in range(len(self.cost)):
+                tr = FrenetTrajectory().fill_from_device_record(out["records"][c], int(self._end[c, 3]),
+                                                                int(n_cart[c]), float(self.cost[c]))
+                if self._idx3 is not None:
+                    tr.idx = np.array(self._idx3[c])
+                items.append(tr)
+            self._items = items
+        return self._items
+
+    def __getitem__(self, i):
+        return self._materialize()[i]
+
+
+# ------------------------------------------------------------------------------------------------
+class FrenetOptimalPlanner(object):
+    def __init__(self, planner_settings: FrenetOptimalPlannerSettings, ego_vehicle: Vehicle, scenario=None,
+                 device: int = 0, engine: FissEngine = None):
+        self.settings = planner_settings
+        self.vehicle = ego_vehicle
+        self.cost_function = CostFunction("WX1")
+        self.cubic_spline = None
+        self.best_traj = None
+        self.all_trajs = []
+        self.stats = Stats()
+        # device side
+        self._device = device
+        self._engine = engine
+        self._obstacle_key = None
+        self._lattice_key = None
+        self._lattice = None
+        self.check_curvature = False  # optional third mask bit; off = reference behaviour (:145-150)
+
+    # -- device plumbing -------------------------------------------------------------------------
+    @property
+    def engine(self) -> FissEngine:
+        if self._engine is None:
+            self._engine = FissEngine(self._device)
+        return self._engine
+
+    def _upload_obstacles(self, obstacles):
+        """Predictions are immutable: re-marshal only when the caller passes a different list."""
+        key = (id(obstacles), len(obstacles))
+        if key != self._obstacle_key:
+            tab = marshal_obstacles(obstacles)
+            if len(tab) == 0:
+                self.engine.set_obstacles(None, np.zeros((0, 2)), None, 0)
+            else:
+                self.engine.set_obstacles(tab.xyth, tab.lw, tab.valid, tab.final_time_step)
+            self._obstacle_key = key
+            self._obstacle_ref = obstacles  # keep the id alive
+
+    def _end_states(self) -> np.ndarray:
+        st = self.settings
+        key = (st.max_road_width, self.vehicle.w, st.num_width, st.min_t, st.max_t, st.num_t, st.lowest_speed,
+               st.highest_speed, st.num_speed, st.tick_t)
+        if key != self._lattice_key:
+            self._lattice = fop_lattice(st, self.vehicle.w)
+            self._lattice_key = key
+        return self._lattice
+
+    def _params(self, time_step_now: int, collide_all: bool = False):
+        return make_params(self.settings, self.vehicle, self.cost_function.as_device_weights(), time_step_now,
+                           check_res=2, check_curvature=self.check_curvature, collide_all=collide_all)
+
+    def _trajectory_from_record(self, rec, meta, cost) -> FrenetTrajectory:
+        return FrenetTrajectory().fill_from_device_record(rec, int(meta[0]), int(meta[1]), float(cost))
+
+    # -- reference API ---------------------------------------------------------------------------
+    def generate_frenet_frame(self, centerline_pts: np.ndarray):
+        """Spline fit on the host (float64, the reference's own dense solve), table upload, and the
+        0.1 m polyline ``[m, 4] = (x, y, yaw, curvature)`` that ``FrenetState.from_state`` consumes
+        (frenet_optimal_planner.py:272-278)."""
+        self.cubic_spline = CubicSpline2D(centerline_pts[:, 0], centerline_pts[:, 1])
+        self.engine.set_spline(self.cubic_spline.device_table())
+        s = np.arange(0, self.cubic_spline.s[-1], 0.1)
+        ref_xy = [self.cubic_spline.calc_position(i_s) for i_s in s]
+        ref_yaw = [self.cubic_spline.calc_yaw(i_s) for i_s in s]
+        ref_rk = [self.cubic_spline.calc_curvature(i_s) for i_s in s]
+        return self.cubic_spline, np.column_stack((ref_xy, ref_yaw, ref_rk))
+
+    def plan(self, frenet_state: FrenetState, max_target_speed: float, obstacles: list, time_step_now: int = 0) -> FrenetTrajectory:
+        self.stats = Stats()
+        self.settings.highest_speed = max_target_speed      # mutates settings, as the reference does (:250)
+        self._upload_obstacles(obstacles)
+        end = self._end_states()
+        prm = self._params(time_step_now)
+        ego6 = frenet_state.as_ego6() if hasattr(frenet_state, "as_ego6") else np.array(
+            [frenet_state.s, frenet_state.s_d, frenet_state.s_dd, frenet_state.d, frenet_state.d_d, frenet_state.d_dd])
+        out = self.engine.plan_lattice(ego6[None], end, prm, want_records=True, want_volume=True)
+
+        n_cand = len(end)
+        self.stats.num_trajs_generated = n_cand
+        self.stats.num_trajs_validated = n_cand
+        self.stats.num_collison_checks = n_cand
+        self.all_trajs.append(CandidateBundle(self.engine, ego6, end, prm, out["cost"][0], out["flags"][0]))
+
+        best = int(out["best_idx"][0])
+        if best >= 0:
+            traj = self._trajectory_from_record(out["records"][0], out["meta"][0], out["best_cost"][0])
+            traj.lattice_index = best
+            self.best_traj = traj
+        # nothing feasible: the previous cycle's best_traj is returned unchanged, like the reference (:263-270)
+        return self.best_traj

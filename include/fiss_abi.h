@@ -1,0 +1,160 @@
+/* fiss_abi.h -- C ABI of libfissgpu.so: the B200 (sm_100a) Frenet lattice engine.
+ *
+ * The reference (SS47816/fiss_plus_planner, pure Python) has no FFI layer; its boundary for this
+ * path is the planner class API.  Each entry point below names the reference
+ * code it replaces (paths relative to the reference root).  Plain pointers and sizes only; no
+ * C++/torch types; every call returns an int32 status (FISS_OK or a negative FISS_ERR_*) and
+ * never lets a C++ exception escape.  A handle is bound to one device, is not thread-safe, and
+ * owns: the uploaded spline and obstacle tables, pinned host staging and device scratch for the
+ * *_host entry points.  The *_dev entry points work on caller-owned device buffers (e.g. torch
+ * tensors' data_ptr()) and are asynchronous on `stream` (a cudaStream_t passed as void*).
+ *
+ * Candidate numbering: candidate (b, c) = problem b in [0, B), end state c in [0, C); flat id
+ * b*C + c.  For FrenetOptimalPlanner the host enumerates end states in the reference's loop order
+ * d (outer), T, v (inner) (frenet_optimal_planner.py:75,78,89), so "last minimal cost wins"
+ * (:263-268) is "largest flat id among the minima".
+ */
+#ifndef FISS_ABI_H_
+#define FISS_ABI_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct fiss_handle fiss_handle;
+
+enum {
+  FISS_OK = 0,
+  FISS_ERR_INVALID = -1,  /* bad argument */
+  FISS_ERR_CUDA = -2,     /* a CUDA runtime call failed; see fiss_last_error */
+  FISS_ERR_CAPACITY = -3, /* request exceeds what one launch supports */
+  FISS_ERR_STATE = -4     /* spline not set, ... */
+};
+
+/* per-candidate flags word written by the device */
+#define FISS_FLAG_SPEED 1u      /* any(s_d > max_speed)        frenet_optimal_planner.py:152 */
+#define FISS_FLAG_ACCEL 2u      /* any(|s_dd| > max_accel)     frenet_optimal_planner.py:155 */
+#define FISS_FLAG_CURVATURE 4u  /* any(|c| > max_curvature); only if check_curvature (off in the reference, :145-150) */
+#define FISS_FLAG_COLLISION 8u  /* has_collision()             frenet_optimal_planner.py:168-195 */
+#define FISS_FLAG_INFEASIBLE_MASK 15u
+#define FISS_FLAG_NCART_SHIFT 8 /* bits 8..23: n' = number of Cartesian points (truncation, :112-113) */
+#define FISS_FLAG_NCART_MASK 0xFFFFu
+
+/* rows of a "full record" [FISS_REC_ROWS][n_stride] (FrenetTrajectory fields, frenet.py:131-148) */
+enum {
+  FISS_REC_T = 0, FISS_REC_S, FISS_REC_S_D, FISS_REC_S_DD, FISS_REC_S_DDD,
+  FISS_REC_D, FISS_REC_D_D, FISS_REC_D_DD, FISS_REC_D_DDD,
+  FISS_REC_X, FISS_REC_Y, FISS_REC_YAW, FISS_REC_DS, FISS_REC_C, FISS_REC_C_D, FISS_REC_C_DD,
+  FISS_REC_ROWS
+};
+
+/* rows of the dense materialisation [FISS_MAT_ROWS][B*C][n_stride]: the output contract
+ * (x, y, yaw, v = s_d, kappa = c) of SURVEY 8(a) row a7 */
+enum { FISS_MAT_X = 0, FISS_MAT_Y, FISS_MAT_YAW, FISS_MAT_V, FISS_MAT_KAPPA, FISS_MAT_ROWS };
+
+/* One POD per launch: the planner settings, vehicle limits and cost weights the path reads. */
+typedef struct fiss_params {
+  double tick_t;           /* settings.tick_t                          frenet_optimal_planner.py:41 */
+  double target_speed;     /* settings.highest_speed (= max_target_speed, :250) -> cost target */
+  double max_speed;        /* vehicle.max_speed                        vehicle.py:39 */
+  double max_accel;        /* vehicle.max_accel                        vehicle.py:40 */
+  double max_curvature;    /* vehicle.max_curvature; used iff check_curvature */
+  double ego_length;       /* vehicle.l                                vehicle.py:17 */
+  double ego_width;        /* vehicle.w                                vehicle.py:18 */
+  double cost_time_offset; /* the literal 10.0 of cost_function.py:42 */
+  double w_speed;          /* w_V = 1      cost_function.py:9  */
+  double w_accel;          /* w_A = 0.1    cost_function.py:10 */
+  double w_jerk;           /* w_J = 0.1    cost_function.py:11 */
+  double w_offset;         /* w_LC = 10    cost_function.py:12 */
+  int32_t time_step_now;   /* plan(..., time_step_now)                 frenet_optimal_planner.py:247 */
+  int32_t check_res;       /* has_collision check_res; the planners pass 2 (:202) */
+  int32_t check_curvature; /* 0 = reference behaviour */
+  int32_t collide_all;     /* 0: collision only for constraint survivors (plan(), :257-259); 1: for every candidate */
+} fiss_params;
+
+/* ---- lifetime / errors ------------------------------------------------------------------- */
+int32_t fiss_create(int32_t device, fiss_handle** out);
+int32_t fiss_destroy(fiss_handle* h);
+/* message of the last failing call on `h` (or of the last failing fiss_create when h == NULL) */
+const char* fiss_last_error(const fiss_handle* h);
+int32_t fiss_abi_version(void);
+
+/* len(np.arange(0.0, T, tick)): the step count n of a candidate with horizon T
+ * (frenet_optimal_planner.py:82, fiss_planner.py:113, fiss_plus_planner.py:181). */
+int32_t fiss_arange_len(double T, double tick);
+
+/* ---- scene tables (host pointers in, copied to handle-owned device memory) ----------------- */
+/* table: [9][K] float64 rows = knots s_k, then a,b,c,d of x(s), then a,b,c,d of y(s)
+ * (CubicSpline2D.sx / .sy, cubic_spline.py:162-168; b and d have K-1 live entries).
+ * Replaces the per-step CubicSpline2D.calc_position / calc_yaw calls (:170-190,214-232). */
+int32_t fiss_set_spline(fiss_handle* h, void* stream, const double* table, int32_t K);
+
+/* Dense obstacle predictions: xyth [M][T_obs][3] = (x, y, orientation) at absolute time step t,
+ * lw [M][2] = rectangle (length, width), valid [M][T_obs] != 0 where obstacle.state_at_time(t)
+ * is not None, final_time_step = obstacles[0].prediction.final_time_step
+ * (frenet_optimal_planner.py:173,185-189).  M == 0 clears the table (no obstacles: :170-171). */
+int32_t fiss_set_obstacles(fiss_handle* h, void* stream, const double* xyth, const double* lw,
+                           const uint8_t* valid, int32_t M, int32_t T_obs, int32_t final_time_step);
+
+/* Same table from the Waymo wire format of waymo_interface.py:24-76,146:
+ * trajs [N][T][11] float32 = (x, y, z, l, w, h, heading, vx, vy, valid, type), mask [N][T];
+ * an obstacle's prediction ends at the first masked step >= 1 (:49-52); length/width from step 0. */
+int32_t fiss_set_obstacles_waymo(fiss_handle* h, void* stream, const float* trajs, const uint8_t* mask,
+                                 int32_t N, int32_t T, int32_t final_time_step);
+
+/* ---- device-pointer API ------------------------------------------------------------------- */
+/* The hot kernel: every candidate (b, c) through quintic/quartic solve, n-step evaluation, cost
+ * (calc_frenet_paths :69-104 + cost_total), Frenet->Cartesian (calc_global_paths :106-138),
+ * constraint masks (:140-160) and collision mask (:168-208).
+ *   d_ego  [B][6]  (s, s_d, s_dd, d, d_d, d_dd)        FrenetState fields read at :81,92
+ *   d_end  [C][4]  (d_end, v_end, T, n) ; n = fiss_arange_len(T, tick_t) stored as a double
+ *   d_cost [B*C], d_flags [B*C]
+ *   d_mat  optional (may be NULL): [FISS_MAT_ROWS][B*C][n_stride] float64, NaN beyond each row's length
+ */
+int32_t fiss_eval_candidates_dev(fiss_handle* h, void* stream, const double* d_ego, int32_t B,
+                                 const double* d_end, int32_t C, const fiss_params* p,
+                                 double* d_cost, uint32_t* d_flags, double* d_mat, int32_t n_stride);
+
+/* argmin with the reference's tie rule (:263-268: `min_cost >= cost` => last minimum wins) over the
+ * feasible candidates of each problem, then the winner's full record.
+ *   d_best_idx [B] (-1 when nothing survives), d_best_cost [B],
+ *   d_records optional [B][FISS_REC_ROWS][n_stride], d_best_meta optional [B][2] = (n, n') */
+int32_t fiss_pick_winners_dev(fiss_handle* h, void* stream, const double* d_ego, int32_t B,
+                              const double* d_end, int32_t C, const fiss_params* p,
+                              const double* d_cost, const uint32_t* d_flags,
+                              int32_t* d_best_idx, double* d_best_cost, double* d_records,
+                              int32_t* d_best_meta, int32_t n_stride);
+
+/* Full records (all FrenetTrajectory arrays) of selected candidates of ONE problem:
+ * generate_trajectory / generate_trajectory_by_end_state + calc_global_paths for a list
+ * (fiss_planner.py:101-138, fiss_plus_planner.py:172-205).  d_sel [N] indexes d_end; NULL = 0..N-1.
+ *   d_records [N][FISS_REC_ROWS][n_stride], d_cost [N], d_flags [N] (masks included) */
+int32_t fiss_full_records_dev(fiss_handle* h, void* stream, const double* d_ego6, const double* d_end,
+                              const int32_t* d_sel, int32_t N, const fiss_params* p,
+                              double* d_records, double* d_cost, uint32_t* d_flags, int32_t n_stride);
+
+/* ---- host-pointer API (what the Python planners and a C caller use) ------------------------ */
+/* plan() for B ego states over one shared lattice: H2D of ego/end states, the hot kernel, the pick
+ * kernel, D2H of winners -- all inside, synchronous on return.
+ *   ego [B][6], end [C][4]; out: best_idx [B], best_cost [B], best_meta [B][2] (n, n'),
+ *   records optional [B][FISS_REC_ROWS][n_stride]; cost / flags optional [B*C] (the whole volume). */
+int32_t fiss_plan_lattice_host(fiss_handle* h, void* stream, const double* ego, int32_t B,
+                               const double* end, int32_t C, const fiss_params* p,
+                               int32_t* best_idx, double* best_cost, int32_t* best_meta,
+                               double* records, int32_t n_stride, double* cost, uint32_t* flags);
+
+/* "evaluate a list of end states" for one ego state: cost + masks for every entry,
+ * and full records when `records` != NULL.  */
+int32_t fiss_eval_end_states_host(fiss_handle* h, void* stream, const double* ego6, const double* end,
+                                  int32_t N, const fiss_params* p, double* cost, uint32_t* flags,
+                                  double* records, int32_t n_stride);
+
+/* number of kernel launches issued through this handle so far (bench.py's gpu_launches) */
+int64_t fiss_launch_count(const fiss_handle* h);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FISS_ABI_H_ */
