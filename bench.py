@@ -1,0 +1,378 @@
+#!/usr/bin/env python
+"""bench.py -- candidate trajectories / s of the Frenet lattice hot path on B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+A "step" is one pass of the hot path over one batch of synthetic ego states: every candidate of a
+9x6x5 (d, v, T) lattice x <=50 time steps against 32 predicted obstacles (BASELINE.json north_star /
+configs[3] per-GPU shard: 512 ego states per GPU, weak scaling -> 4096 on 8 GPUs).
+
+* ``value``   device-resident throughput: ego states already in HBM; the step is the fused lattice
+              kernel in FULL-MATERIALISATION mode (x, y, yaw, v, kappa of every candidate written to
+              HBM, FP64: 276 MB per step per GPU, larger than the 126 MB L2) + the pick kernel + the
+              winners' full records.  CUDA events on the launching stream, max over ranks.
+* ``e2e``     the same metric through the host C-ABI call ``fiss_plan_lattice_host`` with HOST buffers:
+              H2D of the ego states and D2H of winners/records inside the timed region.
+* ``roofline`` the lattice kernel alone: algorithmic bytes (SURVEY 8(d) formula) / its CUDA-event time,
+              against MEASURED_PEAKS.json's HBM copy bandwidth.  The kernel is FP64-issue bound, not
+              HBM bound: the fraction is reported as measured, not dressed up.
+* ``cpu_baseline`` the oracle port of the reference's Python path (oracle/fop_oracle.py), all host cores.
+
+``--impl reference`` times that CPU port alone (the reference itself is Python + commonroad/shapely
+and cannot travel to the GPU box; its hot path is restated in oracle/, pinned by tests/golden).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import multiprocessing as mp
+import os
+import subprocess
+import sys
+import threading
+import time
+import warnings
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+LATTICE = (9, 6, 5)
+MIN_T, MAX_T = 4.0, 5.0
+NUM_OBS = 32
+BATCH_PER_GPU = 512
+METRIC = "candidate_trajectories_per_sec"
+UNIT = "candidates/s"
+
+
+# ------------------------------------------------------------------------------------------------ scene
+def make_workload(n_gpus: int, batch_per_gpu: int):
+    from fiss_plus_planner_b200 import synthetic as syn
+    sc = syn.make_scene("cfg4_batch4096_32obs", batch=batch_per_gpu * n_gpus, num_obstacles=NUM_OBS)
+    return sc
+
+
+def config_dict(n_gpus, batch_per_gpu):
+    return {
+        "workload": "cfg4 shard: %d ego states/GPU x 9x6x5 lattice (270 candidates) x n<=50 steps x %d obstacles "
+                    "(north_star target config; configs[3] = 4096 states on 8 GPUs)" % (batch_per_gpu, NUM_OBS),
+        "lattice": list(LATTICE), "steps_per_candidate": "40..50 (T in [4,5] s, tick 0.1 s)",
+        "obstacles": NUM_OBS, "batch_per_gpu": batch_per_gpu, "global_batch": batch_per_gpu * n_gpus,
+        "parallelism": "problems sharded across %d GPU(s), no data-path collective" % n_gpus,
+        "l2": "per-step output (276 MB/GPU in materialisation mode) exceeds the 126 MB L2",
+    }
+
+
+# ------------------------------------------------------------------------------------------------ CPU baseline
+def cpu_port_rate(sc, steps: int, warmup: int, budget_s: float):
+    """Candidates/s of the oracle port on all host cores.  One step = ONE ego state's 270-candidate
+    lattice split across the cores (FOP plan() semantics)."""
+    from fiss_plus_planner_b200 import synthetic as syn
+    from oracle import fop_oracle as fo
+    cores = os.cpu_count() or 1
+    n_cand = LATTICE[0] * LATTICE[1] * LATTICE[2]
+    workers = min(cores, n_cand)
+    bounds = np.linspace(0, n_cand, workers + 1).astype(int)
+    init = (sc.centerline, (sc.obs.xyth, sc.obs.lw, sc.obs.valid, sc.obs.final_time_step),
+            dict(num_width=LATTICE[0], num_speed=LATTICE[1], num_t=LATTICE[2]), MIN_T, MAX_T, sc.max_target_speed,
+            syn.EGO_L, syn.EGO_W, syn.EGO_V_MAX, syn.EGO_A_MAX)
+    ctx = mp.get_context("fork")
+    times = []
+    with ctx.Pool(workers, initializer=fo.baseline_worker_init, initargs=init) as pool:
+        t_begin = time.perf_counter()
+        for i in range(warmup + steps):
+            ego6 = tuple(float(v) for v in sc.ego[i % len(sc.ego)])
+            tasks = [(ego6, int(bounds[w]), int(bounds[w + 1]), 0) for w in range(workers)]
+            t0 = time.perf_counter()
+            res = pool.map(fo.baseline_worker_slice, tasks, chunksize=1)
+            dt = time.perf_counter() - t0
+            assert sum(r[0] for r in res) == n_cand
+            if i >= warmup:
+                times.append(dt)
+            if time.perf_counter() - t_begin > budget_s and len(times) >= 1:
+                break
+    total = float(np.sum(times))
+    return dict(value=n_cand * len(times) / total, steps_done=len(times), ms_per_step=1e3 * total / len(times),
+                cores=workers,
+                sample="%d step(s); each = one ego state's 270-candidate lattice (n<=50, %d obstacles) split over %d "
+                       "processes; Python port of the reference loops, NumPy SAT in place of shapely/GEOS"
+                       % (len(times), NUM_OBS, workers))
+
+
+# ------------------------------------------------------------------------------------------------ clocks
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.gpu = gpu_index
+        self.rows = []
+        self.proc = None
+        self.thread = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except OSError:
+            self.proc = None
+            return
+        self.thread = threading.Thread(target=self._pump, daemon=True)
+        self.thread.start()
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            f = [x.strip() for x in r.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": float(np.max(mx)) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------ ours
+def algorithmic_bytes(end, batch, num_obs, num_knots):
+    """SURVEY 8(d), full-materialisation FP64: per candidate 5*n*8 + 16; per problem the tables read once."""
+    n = end[:, 3]
+    per_problem_out = float(np.sum(5 * n * 8 + 16))
+    t_chk = np.ceil(n.max() / 2)
+    per_problem_in = 24 * num_obs * t_chk + 16 * num_obs + 72 * num_knots + 48
+    return batch * (per_problem_out + per_problem_in)
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    n_gpus = world
+    bpg = args.batch_per_gpu
+    sc = make_workload(n_gpus, bpg)
+
+    # CPU baseline first (rank 0, N=1 only), before CUDA is initialised in this process (fork-safe)
+    cpu = None
+    if n_gpus == 1 and not args.no_cpu_baseline:
+        cpu = cpu_port_rate(sc, steps=4, warmup=1, budget_s=40.0)
+
+    from fiss_plus_planner_b200.engine import FissEngine, fop_lattice, make_params
+    from fiss_plus_planner_b200.planners.common.cost.cost_function import CostFunction
+    from fiss_plus_planner_b200.planners.common.vehicle.vehicle import Vehicle
+    from fiss_plus_planner_b200.planners.frenet_optimal_planner import FrenetOptimalPlannerSettings
+    from fiss_plus_planner_b200 import synthetic as syn
+
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    veh = Vehicle(syn.vehicle_params())
+    st = FrenetOptimalPlannerSettings(*LATTICE)
+    st.min_t, st.max_t, st.highest_speed = MIN_T, MAX_T, sc.max_target_speed
+    eng = FissEngine(local_rank)
+    eng.set_spline(sc.spline.device_table())
+    eng.set_obstacles(sc.obs.xyth, sc.obs.lw, sc.obs.valid, sc.obs.final_time_step)
+    end = fop_lattice(st, veh.w)
+    prm = make_params(st, veh, CostFunction("WX1").as_device_weights())
+    ego = np.ascontiguousarray(sc.ego[rank * bpg:(rank + 1) * bpg])
+    B, C = ego.shape[0], end.shape[0]
+    n_stride = int(end[:, 3].max())
+
+    stream = torch.cuda.current_stream()
+    sptr = stream.cuda_stream
+    f64 = torch.float64
+    ego_t = torch.tensor(ego, dtype=f64, device=dev)
+    end_t = torch.tensor(end, dtype=f64, device=dev)
+    cost_t = torch.empty(B * C, dtype=f64, device=dev)
+    flags_t = torch.empty(B * C, dtype=torch.int32, device=dev)
+    mat_t = torch.empty((5, B * C, n_stride), dtype=f64, device=dev)
+    bidx_t = torch.empty(B, dtype=torch.int32, device=dev)
+    bcost_t = torch.empty(B, dtype=f64, device=dev)
+    rec_t = torch.empty((B, 16, n_stride), dtype=f64, device=dev)
+    meta_t = torch.empty((B, 2), dtype=torch.int32, device=dev)
+
+    def step_device(mat=mat_t):
+        eng.eval_candidates_dev(ego_t, end_t, prm, cost_t, flags_t, mat, n_stride, stream=sptr)
+        eng.pick_winners_dev(ego_t, end_t, prm, cost_t, flags_t, bidx_t, bcost_t, rec_t, meta_t, n_stride, stream=sptr)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x: float) -> float:
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=f64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    # ---- device-resident timing (value) + the lattice kernel alone (roofline)
+    for _ in range(args.warmup):
+        step_device()
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    launches0 = eng.launch_count
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    k_ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    ev0.record(stream)
+    for i in range(args.steps):
+        k_ev[i][0].record(stream)
+        eng.eval_candidates_dev(ego_t, end_t, prm, cost_t, flags_t, mat_t, n_stride, stream=sptr)
+        k_ev[i][1].record(stream)
+        eng.pick_winners_dev(ego_t, end_t, prm, cost_t, flags_t, bidx_t, bcost_t, rec_t, meta_t, n_stride, stream=sptr)
+    ev1.record(stream)
+    barrier()
+    launches = eng.launch_count - launches0
+    total_ms = max_over_ranks(ev0.elapsed_time(ev1))
+    kern_ms = float(np.mean([a.elapsed_time(b) for a, b in k_ev]))
+
+    # ---- winner-only mode (what plan() strictly needs; reported beside the headline)
+    for _ in range(args.warmup):
+        step_device(None)
+    barrier()
+    ev0.record(stream)
+    for _ in range(args.steps):
+        step_device(None)
+    ev1.record(stream)
+    barrier()
+    wo_ms = max_over_ranks(ev0.elapsed_time(ev1))
+
+    # ---- end to end through the host C-ABI call (H2D + kernels + D2H inside)
+    for _ in range(args.warmup):
+        eng.plan_lattice(ego, end, prm, want_records=True, want_volume=False, stream=sptr)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        out = eng.plan_lattice(ego, end, prm, want_records=True, want_volume=False, stream=sptr)
+    torch.cuda.synchronize()
+    e2e_s = max_over_ranks(time.perf_counter() - t0)
+    # the clock record spans all three timed regions (device-resident, winner-only, end-to-end)
+    clocks = sampler.stop() if rank == 0 else None
+    h2d = B * 48
+    d2h = B * (8 + 4 + 8) + B * 16 * n_stride * 8
+
+    # ---- plan-cycle latency, config 2: ONE ego state, 8 obstacles, through the same host call
+    p50 = None
+    if rank == 0:
+        sc2 = syn.make_scene("cfg2_single_ego_8obs", batch=1)
+        eng2 = FissEngine(local_rank)
+        eng2.set_spline(sc2.spline.device_table())
+        eng2.set_obstacles(sc2.obs.xyth, sc2.obs.lw, sc2.obs.valid, sc2.obs.final_time_step)
+        for _ in range(20):
+            eng2.plan_lattice(sc2.ego[:1], end, prm, want_records=True, want_volume=True, stream=sptr)
+        lat = []
+        for _ in range(200):
+            t1 = time.perf_counter()
+            eng2.plan_lattice(sc2.ego[:1], end, prm, want_records=True, want_volume=True, stream=sptr)
+            lat.append(time.perf_counter() - t1)
+        p50 = 1e3 * float(np.median(lat))
+        eng2.close()
+
+    if rank == 0:
+        peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+        if os.path.exists(peaks_path):
+            peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs (measured)"
+        else:
+            peak, peak_src = 6650.0, "fallback 6.65 TB/s (B200_PROFILING.md)"
+        alg = algorithmic_bytes(end, B, NUM_OBS, len(sc.spline.s))
+        achieved = alg / (kern_ms * 1e-3) / 1e9
+        cand_total = B * C * n_gpus
+        line = {
+            "metric": METRIC, "value": cand_total * args.steps / (total_ms * 1e-3), "unit": UNIT,
+            "n_gpus": n_gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": total_ms / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": config_dict(n_gpus, bpg),
+            "mode": "full materialisation (x,y,yaw,v,kappa of every candidate to HBM, FP64) + pick + winner records",
+            "value_winner_only": cand_total * args.steps / (wo_ms * 1e-3),
+            "e2e": {"value": cand_total * args.steps / e2e_s, "unit": UNIT, "h2d_bytes_per_step": h2d,
+                    "d2h_bytes_per_step": d2h, "ms_per_step": 1e3 * e2e_s / args.steps,
+                    "call": "fiss_plan_lattice_host (host ego states in, winners + full records out)"},
+            "gpu_launches": int(launches),
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": None, "kernel": "fiss_eval_kernel<mat>", "kernel_ms": kern_ms,
+                         "algorithmic_bytes_per_launch": alg, "peak_source": peak_src,
+                         "note": "FP64-issue bound by arithmetic (SURVEY 8(d)); see profiles/ for ncu fp64 pipe utilisation"},
+            "plan_cycle_p50_ms": p50,
+            "plan_cycle_config": "config 2: 1 ego state, 270 candidates, 8 obstacles, fiss_plan_lattice_host incl. H2D/D2H",
+            "clocks": clocks,
+        }
+        if cpu is not None:
+            line["cpu_baseline"] = {"value": cpu["value"], "unit": UNIT, "cores": cpu["cores"], "kind": "port",
+                                    "sample": cpu["sample"]}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+# ------------------------------------------------------------------------------------------------ reference arm
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    n_gpus = int(os.environ.get("WORLD_SIZE", str(args.gpus)))
+    sc = make_workload(1, min(args.batch_per_gpu, 64))
+    # keep the whole run within a few minutes whatever K and W are
+    cpu = cpu_port_rate(sc, steps=args.steps, warmup=args.warmup, budget_s=150.0)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": cpu["value"], "unit": UNIT, "n_gpus": n_gpus,
+        "steps": cpu["steps_done"], "warmup": args.warmup, "ms_per_step": cpu["ms_per_step"],
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": config_dict(n_gpus, args.batch_per_gpu),
+        "cpu_baseline": {"value": cpu["value"], "unit": UNIT, "cores": cpu["cores"], "kind": "port",
+                         "sample": cpu["sample"]},
+        "e2e": {"value": cpu["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+        "note": "the reference is pure Python + commonroad/shapely (not installable here, cannot travel): this arm "
+                "times its hot path as restated in oracle/fop_oracle.py (pinned bit-exact to the reference by "
+                "tests/golden), on all host cores",
+    }
+    print(json.dumps(line))
+
+
+def main():
+    warnings.filterwarnings("ignore")
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch-per-gpu", type=int, default=BATCH_PER_GPU)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -706,3 +706,35 @@ def timed_fop_cycles(ego_batch, settings_kw, centerline, obs_arrays, *, min_t, m
         pl.plan(tuple(ego6), max_target_speed, obs, now)
         n += len(pl.last_all)
     return time.perf_counter() - t0, n
+
+
+# ----------------------------------------------------------------------------------- CPU-baseline workers
+_WORKER = {}
+
+
+def baseline_worker_init(centerline, obs_arrays, settings_kw, min_t, max_t, max_target_speed, ego_l, ego_w,
+                         max_speed, max_accel):
+    """Per-process setup for the timed CPU baseline: spline fit + obstacle table, done once."""
+    st = Settings(**settings_kw)
+    st.min_t, st.max_t, st.highest_speed = min_t, max_t, max_target_speed
+    pl = FopOracle(st, ego_l, ego_w, max_speed, max_accel)
+    pl.generate_frenet_frame(centerline)
+    _WORKER["pl"] = pl
+    _WORKER["lattice"] = pl.lattice()
+    _WORKER["obs"] = ObstacleTable(*obs_arrays) if obs_arrays is not None else None
+
+
+def baseline_worker_slice(task):
+    """FOP semantics (plan(), frenet_optimal_planner.py:252-259) on lattice[lo:hi] of one ego state:
+    generate, convert, constraint mask, collision on the survivors.  Returns (#candidates, best cost, best id)."""
+    ego6, lo, hi, now = task
+    pl = _WORKER["pl"]
+    st = pl.settings
+    best, best_cost = -1, float("inf")
+    for seq in range(lo, hi):
+        d, v, T = _WORKER["lattice"][seq]
+        tr = to_global(generate(Traj(), ego6, d, v, T, st.tick_t, st.highest_speed), pl.spline, st.tick_t)
+        if passes_constraints(tr, pl.max_speed, pl.max_accel) and not has_collision(tr, _WORKER["obs"], pl.ego_ring, now):
+            if best_cost >= tr.cost_final:
+                best_cost, best = tr.cost_final, seq
+    return hi - lo, best_cost, best
