@@ -11,7 +11,7 @@ configs[3] per-GPU shard: 512 ego states per GPU, weak scaling -> 4096 on 8 GPUs
               kernel in FULL-MATERIALISATION mode (x, y, yaw, v, kappa of every candidate written to
               HBM, FP64: 276 MB per step per GPU, larger than the 126 MB L2) + the pick kernel + the
               winners' full records.  CUDA events on the launching stream, max over ranks.
-* ``e2e``     the same metric through the host C-ABI call ``fiss_plan_lattice_host`` with HOST buffers:
+* ``e2e``     the same metric through the host C-ABI call ``fiss_plan_grid_host`` with HOST buffers:
               H2D of the ego states and D2H of winners/records inside the timed region.
 * ``roofline`` the lattice kernel alone: algorithmic bytes (SURVEY 8(d) formula) / its CUDA-event time,
               against MEASURED_PEAKS.json's HBM copy bandwidth.  The kernel is FP64-issue bound, not
@@ -183,7 +183,7 @@ def run_ours(args):
     if n_gpus == 1 and not args.no_cpu_baseline:
         cpu = cpu_port_rate(sc, steps=4, warmup=1, budget_s=40.0)
 
-    from fiss_plus_planner_b200.engine import FissEngine, fop_lattice, make_params
+    from fiss_plus_planner_b200.engine import FissEngine, fop_grid, make_params
     from fiss_plus_planner_b200.planners.common.cost.cost_function import CostFunction
     from fiss_plus_planner_b200.planners.common.vehicle.vehicle import Vehicle
     from fiss_plus_planner_b200.planners.frenet_optimal_planner import FrenetOptimalPlannerSettings
@@ -197,7 +197,8 @@ def run_ours(args):
     eng = FissEngine(local_rank)
     eng.set_spline(sc.spline.device_table())
     eng.set_obstacles(sc.obs.xyth, sc.obs.lw, sc.obs.valid, sc.obs.final_time_step)
-    end = fop_lattice(st, veh.w)
+    grid = fop_grid(st, veh.w)
+    end = grid.table()
     prm = make_params(st, veh, CostFunction("WX1").as_device_weights())
     ego = np.ascontiguousarray(sc.ego[rank * bpg:(rank + 1) * bpg])
     B, C = ego.shape[0], end.shape[0]
@@ -217,7 +218,7 @@ def run_ours(args):
     meta_t = torch.empty((B, 2), dtype=torch.int32, device=dev)
 
     def step_device(mat=mat_t):
-        eng.eval_candidates_dev(ego_t, end_t, prm, cost_t, flags_t, mat, n_stride, stream=sptr)
+        eng.eval_grid_dev(ego_t, grid, prm, cost_t, flags_t, mat, n_stride, stream=sptr)
         eng.pick_winners_dev(ego_t, end_t, prm, cost_t, flags_t, bidx_t, bcost_t, rec_t, meta_t, n_stride, stream=sptr)
 
     def barrier():
@@ -245,7 +246,7 @@ def run_ours(args):
     ev0.record(stream)
     for i in range(args.steps):
         k_ev[i][0].record(stream)
-        eng.eval_candidates_dev(ego_t, end_t, prm, cost_t, flags_t, mat_t, n_stride, stream=sptr)
+        eng.eval_grid_dev(ego_t, grid, prm, cost_t, flags_t, mat_t, n_stride, stream=sptr)
         k_ev[i][1].record(stream)
         eng.pick_winners_dev(ego_t, end_t, prm, cost_t, flags_t, bidx_t, bcost_t, rec_t, meta_t, n_stride, stream=sptr)
     ev1.record(stream)
@@ -267,11 +268,11 @@ def run_ours(args):
 
     # ---- end to end through the host C-ABI call (H2D + kernels + D2H inside)
     for _ in range(args.warmup):
-        eng.plan_lattice(ego, end, prm, want_records=True, want_volume=False, stream=sptr)
+        eng.plan_grid(ego, grid, prm, want_records=True, want_volume=False, stream=sptr)
     barrier()
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        out = eng.plan_lattice(ego, end, prm, want_records=True, want_volume=False, stream=sptr)
+        out = eng.plan_grid(ego, grid, prm, want_records=True, want_volume=False, stream=sptr)
     torch.cuda.synchronize()
     e2e_s = max_over_ranks(time.perf_counter() - t0)
     # the clock record spans all three timed regions (device-resident, winner-only, end-to-end)
@@ -287,11 +288,11 @@ def run_ours(args):
         eng2.set_spline(sc2.spline.device_table())
         eng2.set_obstacles(sc2.obs.xyth, sc2.obs.lw, sc2.obs.valid, sc2.obs.final_time_step)
         for _ in range(20):
-            eng2.plan_lattice(sc2.ego[:1], end, prm, want_records=True, want_volume=True, stream=sptr)
+            eng2.plan_grid(sc2.ego[:1], grid, prm, want_records=True, want_volume=True, stream=sptr)
         lat = []
         for _ in range(200):
             t1 = time.perf_counter()
-            eng2.plan_lattice(sc2.ego[:1], end, prm, want_records=True, want_volume=True, stream=sptr)
+            eng2.plan_grid(sc2.ego[:1], grid, prm, want_records=True, want_volume=True, stream=sptr)
             lat.append(time.perf_counter() - t1)
         p50 = 1e3 * float(np.median(lat))
         eng2.close()
@@ -314,14 +315,14 @@ def run_ours(args):
             "value_winner_only": cand_total * args.steps / (wo_ms * 1e-3),
             "e2e": {"value": cand_total * args.steps / e2e_s, "unit": UNIT, "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": d2h, "ms_per_step": 1e3 * e2e_s / args.steps,
-                    "call": "fiss_plan_lattice_host (host ego states in, winners + full records out)"},
+                    "call": "fiss_plan_grid_host (host ego states in, winners + full records out)"},
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": None, "kernel": "fiss_eval_kernel<mat>", "kernel_ms": kern_ms,
+                         "traffic": None, "kernel": "fiss_grid_kernel<yaw> (materialising)", "kernel_ms": kern_ms,
                          "algorithmic_bytes_per_launch": alg, "peak_source": peak_src,
                          "note": "FP64-issue bound by arithmetic (SURVEY 8(d)); see profiles/ for ncu fp64 pipe utilisation"},
             "plan_cycle_p50_ms": p50,
-            "plan_cycle_config": "config 2: 1 ego state, 270 candidates, 8 obstacles, fiss_plan_lattice_host incl. H2D/D2H",
+            "plan_cycle_config": "config 2: 1 ego state, 270 candidates, 8 obstacles, fiss_plan_grid_host incl. H2D/D2H",
             "clocks": clocks,
         }
         if cpu is not None:

@@ -8,7 +8,8 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libfissgpu.so")
+# FISSGPU_LIB: load another build of the same library (A/B runs of kernel variants on the GPU box)
+LIB_PATH = os.environ.get("FISSGPU_LIB") or os.path.join(_HERE, "libfissgpu.so")
 
 FISS_OK = 0
 FLAG_SPEED, FLAG_ACCEL, FLAG_CURVATURE, FLAG_COLLISION = 1, 2, 4, 8
@@ -20,8 +21,8 @@ MAT_ROWS = 5
 EXPORTS = (
     "fiss_create", "fiss_destroy", "fiss_last_error", "fiss_abi_version", "fiss_arange_len",
     "fiss_set_spline", "fiss_set_obstacles", "fiss_set_obstacles_waymo",
-    "fiss_eval_candidates_dev", "fiss_pick_winners_dev", "fiss_full_records_dev",
-    "fiss_plan_lattice_host", "fiss_eval_end_states_host", "fiss_launch_count",
+    "fiss_eval_candidates_dev", "fiss_eval_grid_dev", "fiss_pick_winners_dev", "fiss_full_records_dev",
+    "fiss_plan_lattice_host", "fiss_plan_grid_host", "fiss_eval_end_states_host", "fiss_launch_count",
 )
 
 
@@ -35,6 +36,18 @@ class FissParams(C.Structure):
         ("time_step_now", C.c_int32), ("check_res", C.c_int32), ("check_curvature", C.c_int32),
         ("collide_all", C.c_int32),
     ]
+
+
+class FissGrid(C.Structure):
+    """struct fiss_grid (fiss_abi.h): the product lattice d_end x v_end x T with its candidate numbering."""
+    _fields_ = [
+        ("d_end", C.POINTER(C.c_double)), ("v_end", C.POINTER(C.c_double)), ("T", C.POINTER(C.c_double)),
+        ("nd", C.c_int32), ("nv", C.c_int32), ("nt", C.c_int32),
+        ("stride_d", C.c_int32), ("stride_v", C.c_int32), ("stride_t", C.c_int32),
+    ]
+
+
+GRID_AXIS_MAX = 64
 
 
 class FissError(RuntimeError):
@@ -57,6 +70,7 @@ def load():
     lib = C.CDLL(LIB_PATH)
     vp, i32, f64 = C.c_void_p, C.c_int32, C.c_double
     pp = C.POINTER(FissParams)
+    gp = C.POINTER(FissGrid)
     sig = {
         "fiss_create": (i32, [i32, C.POINTER(vp)]),
         "fiss_destroy": (i32, [vp]),
@@ -67,6 +81,8 @@ def load():
         "fiss_set_obstacles": (i32, [vp, vp, vp, vp, vp, i32, i32, i32]),
         "fiss_set_obstacles_waymo": (i32, [vp, vp, vp, vp, i32, i32, i32]),
         "fiss_eval_candidates_dev": (i32, [vp, vp, vp, i32, vp, i32, pp, vp, vp, vp, i32]),
+        "fiss_eval_grid_dev": (i32, [vp, vp, vp, i32, gp, pp, vp, vp, vp, i32]),
+        "fiss_plan_grid_host": (i32, [vp, vp, vp, i32, gp, pp, vp, vp, vp, vp, i32, vp, vp]),
         "fiss_pick_winners_dev": (i32, [vp, vp, vp, i32, vp, i32, pp, vp, vp, vp, vp, vp, vp, i32]),
         "fiss_full_records_dev": (i32, [vp, vp, vp, vp, vp, i32, pp, vp, vp, vp, i32]),
         "fiss_plan_lattice_host": (i32, [vp, vp, vp, i32, vp, i32, pp, vp, vp, vp, vp, i32, vp, vp]),

@@ -11,7 +11,7 @@
 #include <string>
 #include <vector>
 
-#include "fiss_kernels.cuh"
+#include "fiss_grid_kernel.cuh"
 
 namespace {
 
@@ -80,7 +80,11 @@ struct fiss_handle {
   DevBuf d_ego, d_end, d_cost, d_flags, d_best_idx, d_best_cost, d_meta, d_records, d_sel;
   PinBuf h_in, h_out;
   std::vector<double> end_cache;
-  size_t smem_attr[4] = {0, 0, 0, 0};
+  // product lattice (fiss_grid): device axes [4][kAxisMax] + the expanded [C][4] table in d_end
+  DevBuf d_axes;
+  std::vector<double> axes_cache;
+  int grid_n_max = 0;
+  size_t smem_attr[8] = {0, 0, 0, 0, 0, 0, 0, 0};
 };
 
 namespace {
@@ -171,12 +175,6 @@ int32_t plan_launch(fiss_handle* h, const fiss_params* p, int64_t total, int n_b
   return FISS_OK;
 }
 
-int max_steps(const double* end, int C) {
-  int n = 0;
-  for (int c = 0; c < C; ++c) n = std::max(n, (int)end[4 * (size_t)c + 3]);
-  return n;
-}
-
 int32_t check_end_states(fiss_handle* h, const double* end, int C, int n_stride) {
   for (int c = 0; c < C; ++c) {
     const double T = end[4 * (size_t)c + 2], n = end[4 * (size_t)c + 3];
@@ -185,6 +183,129 @@ int32_t check_end_states(fiss_handle* h, const double* end, int C, int n_stride)
     if (n > n_stride) return fail(h, FISS_ERR_INVALID, "n_stride is smaller than a candidate's step count");
   }
   return FISS_OK;
+}
+
+
+// ---- product lattice ---------------------------------------------------------------------------
+// Validate a fiss_grid, (re)upload its axes (and the expanded [C][4] end-state table the record kernel
+// indexes) when they changed, and return the largest step count.
+int32_t ensure_grid(fiss_handle* h, cudaStream_t st, const fiss_grid* g, const fiss_params* p, int* n_max_out) {
+  if (!g || !g->d_end || !g->v_end || !g->T) return fail(h, FISS_ERR_INVALID, "grid or one of its axes is NULL");
+  const int nd = g->nd, nv = g->nv, nt = g->nt;
+  if (nd < 1 || nv < 1 || nt < 1 || nd > FISS_GRID_AXIS_MAX || nv > FISS_GRID_AXIS_MAX || nt > FISS_GRID_AXIS_MAX)
+    return fail(h, FISS_ERR_CAPACITY, "grid axes must have 1.." + std::to_string(FISS_GRID_AXIS_MAX) + " points");
+  // the strides must number [0, nd*nv*nt) densely
+  struct Dim { int size, stride; } dims[3] = {{nd, g->stride_d}, {nv, g->stride_v}, {nt, g->stride_t}};
+  std::sort(dims, dims + 3, [](const Dim& x, const Dim& y) { return x.stride < y.stride || (x.stride == y.stride && x.size < y.size); });
+  int64_t expect = 1;
+  for (const Dim& d : dims) {
+    if (d.size > 1 && d.stride != expect) return fail(h, FISS_ERR_INVALID, "grid strides are not a dense numbering");
+    if (d.size > 1) expect *= d.size;
+  }
+  constexpr int A = fiss::kAxisMax;
+  std::vector<double> axes((size_t)4 * A + 6, 0.0);
+  for (int i = 0; i < nd; ++i) axes[i] = g->d_end[i];
+  for (int j = 0; j < nv; ++j) axes[A + j] = g->v_end[j];
+  int n_max = 0;
+  for (int k = 0; k < nt; ++k) {
+    const double T = g->T[k];
+    const int n = fiss_arange_len(T, p->tick_t);
+    if (!(T > 0.0) || n < 1) return fail(h, FISS_ERR_INVALID, "grid horizon " + std::to_string(k) + ": need T > 0 and n >= 1");
+    axes[2 * A + k] = T;
+    axes[3 * A + k] = (double)n;
+    n_max = std::max(n_max, n);
+  }
+  // the cache key also carries the shape and strides
+  double* tail = axes.data() + 4 * A;
+  tail[0] = nd; tail[1] = nv; tail[2] = nt; tail[3] = g->stride_d; tail[4] = g->stride_v; tail[5] = g->stride_t;
+  *n_max_out = n_max;
+  if (axes == h->axes_cache) return FISS_OK;
+  const int C = nd * nv * nt;
+  std::vector<double> end((size_t)C * 4);
+  for (int i = 0; i < nd; ++i)
+    for (int j = 0; j < nv; ++j)
+      for (int k = 0; k < nt; ++k) {
+        double* e = end.data() + 4 * ((size_t)i * g->stride_d + (size_t)j * g->stride_v + (size_t)k * g->stride_t);
+        e[0] = axes[i]; e[1] = axes[A + j]; e[2] = axes[2 * A + k]; e[3] = axes[3 * A + k];
+      }
+  FISS_CUDA(h, h->d_axes.ensure((size_t)4 * A * 8));
+  FISS_CUDA(h, h->d_end.ensure(end.size() * 8));
+  // pageable sources: both copies are complete w.r.t. the host buffers on return, ordered on `st`
+  FISS_CUDA(h, cudaMemcpyAsync(h->d_axes.p, axes.data(), (size_t)4 * A * 8, cudaMemcpyHostToDevice, st));
+  FISS_CUDA(h, cudaMemcpyAsync(h->d_end.p, end.data(), end.size() * 8, cudaMemcpyHostToDevice, st));
+  h->axes_cache = axes;
+  h->end_cache = end;
+  h->grid_n_max = n_max;
+  return FISS_OK;
+}
+
+template <bool kYaw>
+int32_t launch_grid(fiss_handle* h, cudaStream_t st, const fiss::GridArgs& a, size_t smem, int threads, int which) {
+  auto kern = fiss::fiss_grid_kernel<kYaw>;
+  if (smem > h->smem_attr[which]) {
+    FISS_CUDA(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemLimit));
+    h->smem_attr[which] = kSmemLimit;
+  }
+  int occ = 1;
+  FISS_CUDA(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, threads, smem));
+  occ = std::max(occ, 1);
+  const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(a.items, (int64_t)h->sm_count * occ));
+  kern<<<grid, threads, smem, st>>>(a);
+  h->launches++;
+  FISS_CUDA(h, cudaGetLastError());
+  return FISS_OK;
+}
+
+int32_t eval_grid(fiss_handle* h, cudaStream_t st, const double* d_ego, int B, const fiss_grid* g, int n_max,
+                  const fiss_params* p, double* d_cost, uint32_t* d_flags, double* d_mat, int n_stride) {
+  if (h->K < 2) return fail(h, FISS_ERR_STATE, "fiss_set_spline has not been called");
+  if (n_stride < n_max) return fail(h, FISS_ERR_INVALID, "n_stride is smaller than a candidate's step count");
+  fiss::GridArgs a{};
+  a.ego = d_ego;
+  a.axes = h->d_axes.as<double>();
+  a.nd = g->nd; a.nv = g->nv; a.nt = g->nt;
+  a.sd = g->stride_d; a.sv = g->stride_v; a.st = g->stride_t;
+  a.B = B;
+  a.C = g->nd * g->nv * g->nt;
+  a.total = (int64_t)B * a.C;
+  a.p = *p;
+  a.spline = h->spline.as<double>();
+  a.K = h->K;
+  a.Kp = h->Kp;
+  int it = 0;
+  while ((1 << it) < std::max(h->K - 1, 1)) ++it;
+  a.search_iters = it;
+  a.obs_tab = h->obs_tab.as<double>();
+  a.obs_const = h->obs_const.as<double>();
+  a.M = h->M; a.Mp = h->Mp; a.mp_shift = h->mp_shift; a.T_obs = h->T_obs; a.final_time_step = h->final_time_step;
+  a.words = std::max(1, h->Mp / 32);
+  a.n_pad = (n_max + 2) & ~1;
+  a.e_pad = (n_max + p->check_res - 1) / p->check_res;
+  a.cost = d_cost; a.flags = d_flags; a.mat = d_mat; a.n_stride = n_stride;
+  // work items: (ego state, horizon[, chunk of lateral rows]).  With few ego states the lateral axis is
+  // split so that the launch still covers the SMs (the longitudinal rows are recomputed per chunk).
+  const int64_t base_items = (int64_t)B * g->nt;
+  const int64_t want = 2 * (int64_t)h->sm_count;
+  int chunks = (int)std::min<int64_t>(g->nd, std::max<int64_t>(1, (want + base_items - 1) / base_items));
+  a.d_chunk = std::max(1, g->nd / chunks);
+  a.n_chunks = (g->nd + a.d_chunk - 1) / a.d_chunk;
+  a.items = base_items * a.n_chunks;
+  const int warps = std::max(1, std::min(fiss::kGridWarps, std::max(g->nv + a.d_chunk, a.d_chunk * g->nv)));
+  // obstacle rows of the checked steps go to shared memory while the CTA stays under the budget
+  const int horizon = std::max(0, std::min(n_max, h->final_time_step - p->time_step_now));
+  const int E_max = h->M > 0 ? (horizon + p->check_res - 1) / p->check_res : 0;
+  a.E_stage = E_max;
+  fiss::GridLayout L = fiss::grid_layout(a.Kp, a.Mp, a.E_stage, a.nv, a.d_chunk, a.n_pad, a.e_pad, a.words);
+  if (L.bytes > kSmemObsBudget && a.E_stage > 0) {
+    fiss::GridLayout L0 = fiss::grid_layout(a.Kp, a.Mp, 0, a.nv, a.d_chunk, a.n_pad, a.e_pad, a.words);
+    if (L.bytes > kSmemLimit || L0.bytes + (size_t)E_max * a.Mp * 32 > kSmemLimit) {
+      a.E_stage = 0;
+      L = L0;
+    }
+  }
+  if (L.bytes > kSmemLimit) return fail(h, FISS_ERR_CAPACITY, "lattice row tables exceed 227 KB of shared memory");
+  const bool yaw = d_mat != nullptr || p->check_curvature;
+  return yaw ? launch_grid<true>(h, st, a, L.bytes, warps * 32, 4) : launch_grid<false>(h, st, a, L.bytes, warps * 32, 3);
 }
 
 }  // namespace
@@ -231,7 +352,7 @@ int32_t fiss_destroy(fiss_handle* h) {
   cudaSetDevice(h->device);
   for (DevBuf* b : {&h->spline, &h->obs_tab, &h->obs_const, &h->obs_raw, &h->obs_lw, &h->obs_valid, &h->d_ego,
                     &h->d_end, &h->d_cost, &h->d_flags, &h->d_best_idx, &h->d_best_cost, &h->d_meta, &h->d_records,
-                    &h->d_sel})
+                    &h->d_sel, &h->d_axes})
     b->release();
   h->h_in.release();
   h->h_out.release();
@@ -438,23 +559,20 @@ static int32_t upload_end_states(fiss_handle* h, cudaStream_t st, const double* 
   if (h->end_cache.size() == (size_t)C * 4 && std::memcmp(h->end_cache.data(), end, bytes) == 0) return FISS_OK;
   FISS_CUDA(h, h->d_end.ensure(bytes));
   h->end_cache.assign(end, end + (size_t)C * 4);
+  h->axes_cache.clear();  // d_end is shared with the lattice path
   // the cache vector is pageable memory: the copy is synchronous w.r.t. the host buffer, ordered on `st`
   FISS_CUDA(h, cudaMemcpyAsync(h->d_end.p, h->end_cache.data(), bytes, cudaMemcpyHostToDevice, st));
   return FISS_OK;
 }
 
-int32_t fiss_plan_lattice_host(fiss_handle* h, void* stream, const double* ego, int32_t B, const double* end,
-                               int32_t C, const fiss_params* p, int32_t* best_idx, double* best_cost,
-                               int32_t* best_meta, double* records, int32_t n_stride, double* cost, uint32_t* flags) {
-  if (!h) return FISS_ERR_INVALID;
-  if (!ego || !end || !best_idx || !best_cost || B < 1 || C < 1)
-    return fail(h, FISS_ERR_INVALID, "plan_lattice: bad arguments");
-  int32_t rc = check_params(h, p);
-  if (rc != FISS_OK) return rc;
-  rc = check_end_states(h, end, C, n_stride);
-  if (rc != FISS_OK) return rc;
-  FISS_CUDA(h, cudaSetDevice(h->device));
-  cudaStream_t st = (cudaStream_t)stream;
+// Shared tail of the two plan entry points: H2D of the ego states, the hot kernel (lattice kernel when
+// `g` is given, generic list kernel otherwise; the [C][4] table is already in h->d_end), the pick, the
+// winners' records and the D2H of everything the caller asked for.  Synchronous on return.
+static int32_t plan_common(fiss_handle* h, cudaStream_t st, const double* ego, int32_t B, int32_t C,
+                           const fiss_grid* g, int n_max, const fiss_params* p, int32_t* best_idx, double* best_cost,
+                           int32_t* best_meta, double* records, int32_t n_stride, double* cost, uint32_t* flags) {
+  int32_t rc;
+  void* stream = (void*)st;
   const size_t total = (size_t)B * C;
   const size_t rec_doubles = records ? (size_t)B * FISS_REC_ROWS * n_stride : 0;
   FISS_CUDA(h, h->d_ego.ensure((size_t)B * 48));
@@ -473,10 +591,13 @@ int32_t fiss_plan_lattice_host(fiss_handle* h, void* stream, const double* ego, 
   char* ho = h->h_out.as<char>();
   std::memcpy(h->h_in.p, ego, (size_t)B * 48);
   FISS_CUDA(h, cudaMemcpyAsync(h->d_ego.p, h->h_in.p, (size_t)B * 48, cudaMemcpyHostToDevice, st));
-  rc = upload_end_states(h, st, end, C);
-  if (rc != FISS_OK) return rc;
-  rc = fiss_eval_candidates_dev(h, stream, h->d_ego.as<double>(), B, h->d_end.as<double>(), C, p,
-                                h->d_cost.as<double>(), h->d_flags.as<uint32_t>(), nullptr, n_stride);
+  if (g) {
+    rc = eval_grid(h, st, h->d_ego.as<double>(), B, g, n_max, p, h->d_cost.as<double>(), h->d_flags.as<uint32_t>(),
+                   nullptr, n_stride);
+  } else {
+    rc = fiss_eval_candidates_dev(h, stream, h->d_ego.as<double>(), B, h->d_end.as<double>(), C, p,
+                                  h->d_cost.as<double>(), h->d_flags.as<uint32_t>(), nullptr, n_stride);
+  }
   if (rc != FISS_OK) return rc;
   rc = fiss_pick_winners_dev(h, stream, h->d_ego.as<double>(), B, h->d_end.as<double>(), C, p,
                              h->d_cost.as<double>(), h->d_flags.as<uint32_t>(), h->d_best_idx.as<int32_t>(),
@@ -497,6 +618,53 @@ int32_t fiss_plan_lattice_host(fiss_handle* h, void* stream, const double* ego, 
   if (cost) std::memcpy(cost, ho + o_vol, total * 8);
   if (flags) std::memcpy(flags, ho + o_flags, total * 4);
   return FISS_OK;
+}
+
+int32_t fiss_plan_lattice_host(fiss_handle* h, void* stream, const double* ego, int32_t B, const double* end,
+                               int32_t C, const fiss_params* p, int32_t* best_idx, double* best_cost,
+                               int32_t* best_meta, double* records, int32_t n_stride, double* cost, uint32_t* flags) {
+  if (!h) return FISS_ERR_INVALID;
+  if (!ego || !end || !best_idx || !best_cost || B < 1 || C < 1)
+    return fail(h, FISS_ERR_INVALID, "plan_lattice: bad arguments");
+  int32_t rc = check_params(h, p);
+  if (rc != FISS_OK) return rc;
+  rc = check_end_states(h, end, C, n_stride);
+  if (rc != FISS_OK) return rc;
+  FISS_CUDA(h, cudaSetDevice(h->device));
+  cudaStream_t st = (cudaStream_t)stream;
+  rc = upload_end_states(h, st, end, C);
+  if (rc != FISS_OK) return rc;
+  return plan_common(h, st, ego, B, C, nullptr, 0, p, best_idx, best_cost, best_meta, records, n_stride, cost, flags);
+}
+
+int32_t fiss_eval_grid_dev(fiss_handle* h, void* stream, const double* d_ego, int32_t B, const fiss_grid* g,
+                           const fiss_params* p, double* d_cost, uint32_t* d_flags, double* d_mat, int32_t n_stride) {
+  if (!h) return FISS_ERR_INVALID;
+  if (!d_ego || !d_cost || !d_flags || B < 1) return fail(h, FISS_ERR_INVALID, "eval_grid: bad arguments");
+  int32_t rc = check_params(h, p);
+  if (rc != FISS_OK) return rc;
+  FISS_CUDA(h, cudaSetDevice(h->device));
+  int n_max = 0;
+  rc = ensure_grid(h, (cudaStream_t)stream, g, p, &n_max);
+  if (rc != FISS_OK) return rc;
+  return eval_grid(h, (cudaStream_t)stream, d_ego, B, g, n_max, p, d_cost, d_flags, d_mat, n_stride);
+}
+
+int32_t fiss_plan_grid_host(fiss_handle* h, void* stream, const double* ego, int32_t B, const fiss_grid* g,
+                            const fiss_params* p, int32_t* best_idx, double* best_cost, int32_t* best_meta,
+                            double* records, int32_t n_stride, double* cost, uint32_t* flags) {
+  if (!h) return FISS_ERR_INVALID;
+  if (!ego || !best_idx || !best_cost || B < 1) return fail(h, FISS_ERR_INVALID, "plan_grid: bad arguments");
+  int32_t rc = check_params(h, p);
+  if (rc != FISS_OK) return rc;
+  FISS_CUDA(h, cudaSetDevice(h->device));
+  cudaStream_t st = (cudaStream_t)stream;
+  int n_max = 0;
+  rc = ensure_grid(h, st, g, p, &n_max);
+  if (rc != FISS_OK) return rc;
+  if (n_stride < n_max) return fail(h, FISS_ERR_INVALID, "n_stride is smaller than a candidate's step count");
+  const int C = g->nd * g->nv * g->nt;
+  return plan_common(h, st, ego, B, C, g, n_max, p, best_idx, best_cost, best_meta, records, n_stride, cost, flags);
 }
 
 int32_t fiss_eval_end_states_host(fiss_handle* h, void* stream, const double* ego6, const double* end, int32_t N,

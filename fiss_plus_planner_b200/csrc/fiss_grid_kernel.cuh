@@ -1,0 +1,502 @@
+// fiss_grid_kernel.cuh -- the lattice ("grid") kernel: the hot path when the end states form the
+// product lattice d_end x v_end x T that FrenetOptimalPlanner / FopPlusPlanner / FissPlanner sample
+// (frenet_optimal_planner.py:72-101, fiss_planner.py:33-99).
+//
+// The reference evaluates every (d, v, T) candidate from scratch.  On the lattice most of that work
+// is shared: the longitudinal quartic s(t) -- and with it the reference-line frame (spline segment
+// search, position, unit tangent), the speed / acceleration masks, the truncation length n' and the
+// longitudinal cost terms -- depends on (v_end, T) only; the lateral quintic d(t) and its cost
+// terms depend on (d_end, T) only.  One work item = (ego state b, horizon T_k[, a chunk of lateral
+// rows]); a persistent CTA
+//
+//   stage 0  (once per CTA) bulk-TMA the spline table [mbarrier 0] and the checked obstacle rows
+//            [mbarrier 1] into shared memory; stage A starts as soon as the spline has landed
+//   stage A  one warp per row, lanes stride over time steps:
+//              longitudinal rows (nv): quartic solve + evaluation, masks, cost terms, frame -> smem
+//                                      tables PX, PY, UX, UY (unit tangent), SD          polynomial.py:5-41
+//              lateral rows (chunk)  : quintic solve + evaluation, cost terms -> smem table D polynomial.py:45-84
+//   stage A' proximity masks: for every (longitudinal row, checked step) a bit per obstacle whose
+//            centre is within (max|d| + r_ego + r_obs) of the FRAME point -- a superset of the
+//            obstacles any candidate on that row can touch at that step (one ballot per pair); the
+//            (row, step) pairs with any bit set are appended to a compact work list
+//   stage B  collision: one LANE per (lateral row, listed pair): ego pose from the tables, then the exact
+//            predicate (circle reject + closed-set SAT, :168-195) for the listed obstacles only
+//            materialisation (when asked): one warp per candidate (i_d, j_v), lanes stride over time
+//            steps: x = PX - D*UY, y = PY + D*UX, heading / ds / kappa by finite differences
+//            (frenet_optimal_planner.py:121-134), the five output rows streamed to HBM
+//   stage C  one lane per candidate: cost = (lon + lat terms)/n, flags word
+//
+// so a candidate costs ~2 table reads per step instead of two polynomial solves, a 7-step segment
+// search and an M x n/2 obstacle sweep.  All arithmetic is FP64 with the same expressions as the
+// generic kernel in fiss_kernels.cuh (masks, n' and winners are bit-identical between the two).
+#pragma once
+
+#include "fiss_kernels.cuh"
+#include "fiss_math.cuh"
+
+namespace fiss {
+
+constexpr int kGridWarps = 8;
+constexpr int kGridThreads = kGridWarps * 32;
+#ifndef FISS_GRID_MIN_CTAS
+#define FISS_GRID_MIN_CTAS 3
+#endif
+constexpr int kGridMinCtas = FISS_GRID_MIN_CTAS;  // resident CTAs per SM the register budget is capped for
+constexpr int kAxisMax = 64;  // lattice points per axis
+
+struct GridArgs {
+  const double* ego;   // [B][6]
+  const double* axes;  // [4][kAxisMax]: d_end, v_end, T, n (step count as a double)
+  int32_t nd, nv, nt;
+  int32_t sd, sv, st;  // candidate c = i_d*sd + j_v*sv + k_t*st
+  int32_t B, C;
+  int32_t d_chunk;     // lateral rows per work item
+  int32_t n_chunks;
+  int64_t items;       // B * nt * n_chunks
+  int64_t total;       // B * C
+  fiss_params p;
+  const double* spline;  // [9][Kp]
+  int32_t K, Kp, search_iters;
+  const double* obs_tab;    // [T_obs][4][Mp]
+  const double* obs_const;  // [4][Mp]
+  int32_t M, Mp, mp_shift, T_obs, final_time_step;
+  int32_t E_stage;     // obstacle rows staged in shared memory (0: read them from global/L2)
+  int32_t words;       // 32-bit mask words per (row, step) = max(1, Mp/32)
+  int32_t n_pad;       // table row length (>= max n + 1, even)
+  int32_t e_pad;       // mask row length (>= max checked steps)
+  double* cost;        // [B*C]
+  uint32_t* flags;     // [B*C]
+  double* mat;         // [5][B*C][n_stride] or NULL
+  int32_t n_stride;
+};
+
+// Shared-memory carve-up (byte offsets, 16-byte aligned), used by the host for the launch size too.
+struct GridLayout {
+  uint32_t spline, oc, obs, axes, lon, lat, lon_cost, lat_cost, dmax, lon_viol, lon_ncart, lon_E, npairs, pairs, cflags, masks, bytes;
+};
+
+__host__ __device__ inline uint32_t grid_align16(uint32_t v) { return (v + 15u) & ~15u; }
+
+__host__ __device__ inline GridLayout grid_layout(int Kp, int Mp, int E_stage, int nv, int d_chunk, int n_pad,
+                                                  int e_pad, int words) {
+  GridLayout L;
+  uint32_t o = 16;  // two mbarriers
+  L.spline = o;     o += 9u * Kp * 8u;
+  L.oc = o;         o += 4u * Mp * 8u;
+  L.obs = o;        o += (uint32_t)E_stage * 4u * Mp * 8u;
+  L.axes = o;       o += 4u * kAxisMax * 8u;
+  L.lon = o;        o += 5u * nv * n_pad * 8u;
+  L.lat = o;        o += (uint32_t)d_chunk * n_pad * 8u;
+  L.lon_cost = o;   o += grid_align16(nv * 8u);
+  L.lat_cost = o;   o += grid_align16(d_chunk * 8u);
+  L.dmax = o;       o += 16;
+  L.lon_viol = o;   o += grid_align16(nv * 4u);
+  L.lon_ncart = o;  o += grid_align16(nv * 4u);
+  L.lon_E = o;      o += grid_align16(nv * 4u);
+  L.npairs = o;     o += 16;
+  L.pairs = o;      o += grid_align16((uint32_t)nv * e_pad * 4u);
+  L.cflags = o;     o += grid_align16((uint32_t)d_chunk * nv * 4u);
+  L.masks = o;      o += grid_align16((uint32_t)nv * e_pad * words * 4u);
+  L.bytes = o;
+  return L;
+}
+
+// Candidate position at step m from the row tables (same expression as the generic kernel:
+// x = px - d*(ty*r), y = py + d*(tx*r) with the unit tangent stored already multiplied out).
+__device__ __forceinline__ void grid_pos(const double* __restrict__ PX, const double* __restrict__ PY,
+                                         const double* __restrict__ UX, const double* __restrict__ UY,
+                                         const double* __restrict__ D, int m, double& x, double& y) {
+  const double d = D[m];
+  x = PX[m] - d * UY[m];
+  y = PY[m] + d * UX[m];
+}
+
+template <bool kYaw>
+__global__ void __launch_bounds__(kGridThreads, kGridMinCtas) fiss_grid_kernel(const GridArgs a) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const GridLayout L = grid_layout(a.Kp, a.Mp, a.E_stage, a.nv, a.d_chunk, a.n_pad, a.e_pad, a.words);
+  uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw);  // [0] spline, [1] obstacles
+  double* sp = reinterpret_cast<double*>(smem_raw + L.spline);
+  double* oc = reinterpret_cast<double*>(smem_raw + L.oc);
+  double* obs_s = reinterpret_cast<double*>(smem_raw + L.obs);
+  double* ax = reinterpret_cast<double*>(smem_raw + L.axes);
+  double* lon = reinterpret_cast<double*>(smem_raw + L.lon);
+  double* lat = reinterpret_cast<double*>(smem_raw + L.lat);
+  double* lon_cost = reinterpret_cast<double*>(smem_raw + L.lon_cost);
+  double* lat_cost = reinterpret_cast<double*>(smem_raw + L.lat_cost);
+  unsigned long long* dmax_bits = reinterpret_cast<unsigned long long*>(smem_raw + L.dmax);
+  uint32_t* lon_viol = reinterpret_cast<uint32_t*>(smem_raw + L.lon_viol);
+  int32_t* lon_ncart = reinterpret_cast<int32_t*>(smem_raw + L.lon_ncart);
+  int32_t* lon_E = reinterpret_cast<int32_t*>(smem_raw + L.lon_E);        // checked steps of the row
+  uint32_t* npairs = reinterpret_cast<uint32_t*>(smem_raw + L.npairs);    // length of the work list
+  uint32_t* pairs = reinterpret_cast<uint32_t*>(smem_raw + L.pairs);      // (row << 16 | checked step) with any proximity bit
+  uint32_t* cflags = reinterpret_cast<uint32_t*>(smem_raw + L.cflags);    // per candidate: collision / curvature bits
+  uint32_t* masks = reinterpret_cast<uint32_t*>(smem_raw + L.masks);
+
+  const fiss_params& p = a.p;
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int wpc = blockDim.x >> 5;
+  const int n_pad = a.n_pad;
+  const int Mp = a.Mp;
+  const int row_len = a.nv * n_pad;  // one longitudinal table
+  double* PX = lon;
+  double* PY = lon + row_len;
+  double* UX = lon + 2 * row_len;
+  double* UY = lon + 3 * row_len;
+  double* SD = lon + 4 * row_len;
+
+  // ---- stage 0: tables.  The spline is needed first (stage A); the obstacle rows only in stage A'.
+  if (threadIdx.x == 0) {
+    mbar_init(&bar[0], 1);
+    mbar_init(&bar[1], 1);
+    fence_mbar_init();
+  }
+  __syncthreads();
+  const uint32_t row_bytes = 4u * Mp * 8u;
+  int rows_live = 0;  // staged rows that exist in the table (time < T_obs)
+  for (int e = 0; e < a.E_stage; ++e)
+    if (p.time_step_now + e * p.check_res < a.T_obs) rows_live = e + 1;
+  if (threadIdx.x == 0) {
+    const uint32_t spline_bytes = 9u * a.Kp * 8u;
+    mbar_expect_tx(&bar[0], spline_bytes);
+    bulk_g2s(sp, a.spline, spline_bytes, &bar[0]);
+    mbar_expect_tx(&bar[1], (Mp > 0 ? row_bytes : 0u) + (uint32_t)rows_live * row_bytes);
+    if (Mp > 0) bulk_g2s(oc, a.obs_const, row_bytes, &bar[1]);
+    for (int e = 0; e < rows_live; ++e)
+      bulk_g2s(obs_s + (int64_t)e * 4 * Mp, a.obs_tab + (int64_t)(p.time_step_now + e * p.check_res) * 4 * Mp,
+               row_bytes, &bar[1]);
+  }
+  // staged rows past the end of the predictions: nobody has a state there (state_at_time -> None)
+  for (int64_t q = (int64_t)rows_live * 4 * Mp + threadIdx.x; q < (int64_t)a.E_stage * 4 * Mp; q += blockDim.x)
+    obs_s[q] = (((q / Mp) & 3) < 2) ? kObsFar : 0.0;
+  for (int q = threadIdx.x; q < 4 * kAxisMax; q += blockDim.x) ax[q] = a.axes[q];
+  mbar_wait(&bar[0], 0);
+  bool obstacles_ready = false;
+
+  const double* obs = a.E_stage > 0 ? obs_s : a.obs_tab;
+  const int obs_row0 = a.E_stage > 0 ? 0 : p.time_step_now;
+  const int obs_row_step = a.E_stage > 0 ? 1 : p.check_res;
+  const double hle = 0.5 * p.ego_length, hwe = 0.5 * p.ego_width;
+  const double re = sqrt(hle * hle + hwe * hwe);
+
+  const int nv = a.nv;
+  const uint32_t nv_magic = (1u << 20) / (uint32_t)nv + 1u;  // c / nv == (c * magic) >> 20 for c < 2^20 / nv
+  const int e_pad = a.e_pad;
+  const int words = a.words;
+  const int res = p.check_res;
+  const int t_left = a.final_time_step - p.time_step_now;
+  const uint32_t n_items = (uint32_t)a.items;
+  const uint32_t n_chunks = (uint32_t)a.n_chunks, nt = (uint32_t)a.nt;
+  const int64_t row_pitch = a.total * a.n_stride;  // distance between two materialised rows
+
+  for (uint32_t item = blockIdx.x; item < n_items; item += gridDim.x) {
+    const uint32_t bk = item / n_chunks;
+    const int chunk = (int)(item - bk * n_chunks);
+    const int b = (int)(bk / nt);
+    const int k = (int)(bk - (uint32_t)b * nt);
+    const int i0 = chunk * a.d_chunk;
+    const int rows_i = min(a.d_chunk, a.nd - i0);
+    const int n_cand = rows_i * nv;
+
+    __syncthreads();  // the previous item's readers are done with the tables (and ax[] is visible)
+    if (threadIdx.x == 0) {
+      *dmax_bits = 0ull;
+      *npairs = 0u;
+    }
+    for (int q = threadIdx.x; q < n_cand; q += blockDim.x) cflags[q] = 0u;
+    const double T = ax[2 * kAxisMax + k];
+    const int n = (int)ax[3 * kAxisMax + k];
+    const double* ego = a.ego + 6 * (int64_t)b;
+    const double s0 = ego[0], v0 = ego[1], a0 = ego[2], d0 = ego[3], dv0 = ego[4], da0 = ego[5];
+    const double T2 = T * T, T3 = T2 * T;
+    __syncthreads();
+
+    // ---- stage A: one warp per row
+    for (int task = warp; task < nv + rows_i; task += wpc) {
+      if (task < nv) {
+        // longitudinal quartic, end (v_end, 0)                      polynomial.py:5-19 (SURVEY A.2 closed form)
+        const int j = task;
+        const double v_end = ax[kAxisMax + j];
+        const double qa2 = 0.5 * a0;
+        const double Vq = v_end - v0 - 2.0 * qa2 * T;
+        const double Aq = -2.0 * qa2;
+        const double qa3 = (3.0 * Vq - Aq * T) / (3.0 * T2);
+        const double qa4 = (Aq * T - 2.0 * Vq) / (4.0 * T3);
+        double acc = 0.0;
+        unsigned viol = 0;
+        int first_bad = n;
+        const int base = j * n_pad;
+        for (int m = lane; m < n; m += 32) {
+          const double t = m * p.tick_t;  // np.arange: start + m*step
+          const double t2 = t * t, t3 = t2 * t, t4 = t3 * t;
+          const double s = s0 + v0 * t + qa2 * t2 + qa3 * t3 + qa4 * t4;
+          const double s_d = v0 + 2.0 * qa2 * t + 3.0 * qa3 * t2 + 4.0 * qa4 * t3;
+          const double s_dd = 2.0 * qa2 + 6.0 * qa3 * t + 12.0 * qa4 * t2;
+          const double s_ddd = 6.0 * qa3 + 24.0 * qa4 * t;
+          const double dv = s_d - p.target_speed;
+          acc += p.w_speed * (dv * dv) + p.w_accel * (s_dd * s_dd) + p.w_jerk * (s_ddd * s_ddd);  // cost_function.py:43-46
+          if (s_d > p.max_speed) viol |= FISS_FLAG_SPEED;         // frenet_optimal_planner.py:152
+          if (fabs(s_dd) > p.max_accel) viol |= FISS_FLAG_ACCEL;  // :155
+          double px, py, tx, ty;
+          if (spline_frame(sp, a.K, a.Kp, a.search_iters, s, px, py, tx, ty)) {
+            const double r = rsqrt(tx * tx + ty * ty);
+            PX[base + m] = px;
+            PY[base + m] = py;
+            UX[base + m] = tx * r;
+            UY[base + m] = ty * r;
+          } else {
+            first_bad = min(first_bad, m);
+          }
+          SD[base + m] = s_d;
+        }
+        acc = warp_sum(acc);
+        viol = warp_or(viol);
+        const int n_cart = warp_min(first_bad);  // n' (:112-113)
+        if (lane == 0) {
+          lon_cost[j] = acc;
+          lon_viol[j] = viol;
+          lon_ncart[j] = n_cart;
+          // checked steps i = e*check_res < t_step_max = min(n', final_time_step - now) (:173-176);
+          // none when the collision stage is skipped for the row (:257-259) or cannot run (n' < 2)
+          const int horizon = min(n_cart, t_left);
+          const bool do_coll = a.M > 0 && horizon > 0 && n_cart >= 2 && (p.collide_all || viol == 0);
+          lon_E[j] = do_coll ? (horizon + res - 1) / res : 0;
+        }
+      } else {
+        // lateral quintic, end (d_end, 0, 0)                        polynomial.py:45-62
+        const int ii = task - nv;
+        const double d_end = ax[i0 + ii];
+        const double iT = 1.0 / T;
+        const double iT2 = iT * iT, iT3 = iT2 * iT;
+        const double la2 = 0.5 * da0;
+        const double Dl = d_end - d0 - dv0 * T - la2 * T2;
+        const double Vl = -dv0 - 2.0 * la2 * T;
+        const double Al = -2.0 * la2;
+        const double la3 = (10.0 * Dl - 4.0 * Vl * T + 0.5 * Al * T2) * iT3;
+        const double la4 = (-15.0 * Dl + 7.0 * Vl * T - Al * T2) * (iT3 * iT);
+        const double la5 = (6.0 * Dl - 3.0 * Vl * T + 0.5 * Al * T2) * (iT3 * iT2);
+        double acc = 0.0, dmax = 0.0;
+        const int base = ii * n_pad;
+        for (int m = lane; m < n; m += 32) {
+          const double t = m * p.tick_t;
+          const double t2 = t * t, t3 = t2 * t, t4 = t3 * t, t5 = t4 * t;
+          const double d = d0 + dv0 * t + la2 * t2 + la3 * t3 + la4 * t4 + la5 * t5;
+          const double d_dd = 2.0 * la2 + 6.0 * la3 * t + 12.0 * la4 * t2 + 20.0 * la5 * t3;
+          const double d_ddd = 6.0 * la3 + 24.0 * la4 * t + 60.0 * la5 * t2;
+          acc += p.w_accel * (d_dd * d_dd) + p.w_jerk * (d_ddd * d_ddd) + p.w_offset * (d * d);  // cost_function.py:45-47
+          dmax = fmax(dmax, fabs(d));  // NaN-ignoring: a NaN row has no frame anyway
+          lat[base + m] = d;
+        }
+        acc = warp_sum(acc);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) dmax = fmax(dmax, __shfl_xor_sync(kFull, dmax, o));
+        if (lane == 0) {
+          lat_cost[ii] = acc;
+          atomicMax(dmax_bits, (unsigned long long)__double_as_longlong(dmax));  // non-negative doubles order as integers
+        }
+      }
+    }
+    __syncthreads();
+
+    // ---- stage A': proximity masks.  Lanes = obstacles; a warp takes checked steps, keeps the obstacle
+    // centres of that step in registers and walks the longitudinal rows: one ballot per (row, step).
+    if (a.M > 0) {
+      if (!obstacles_ready) {
+        mbar_wait(&bar[1], 0);
+        obstacles_ready = true;
+      }
+      const double dmax = __longlong_as_double((long long)*dmax_bits);
+      const double reach0 = (dmax + re) * (1.0 + 1.0e-9) + 1.0e-9;
+      if (Mp <= 32) {
+        const int jo = lane & (Mp - 1);
+        const int sub = lane >> a.mp_shift;
+        const int ppi = 32 >> a.mp_shift;  // checked steps per warp iteration
+        const double reach = reach0 + oc[2 * Mp + jo] * (1.0 + 1.0e-9);
+        const double reach2 = reach * reach;
+        const uint32_t sub_mask = Mp == 32 ? 0xffffffffu : ((1u << Mp) - 1u);
+        const int sub_shift = sub * Mp;
+        for (int e0 = warp * ppi; e0 < e_pad; e0 += wpc * ppi) {
+          const int e = e0 + sub;
+          const int row = obs_row0 + e * obs_row_step;
+          const bool in_tab = a.E_stage > 0 ? e < a.E_stage : (e < e_pad && row < a.T_obs);
+          const double* slot = obs + row * (4 * Mp) + jo;
+          const double ox = in_tab ? slot[0] : kObsFar, oy = in_tab ? slot[Mp] : kObsFar;
+          const int m = min(e * res, n_pad - 1);
+          for (int j = 0; j < nv; ++j) {
+            const double dx = ox - PX[j * n_pad + m], dy = oy - PY[j * n_pad + m];
+            const bool near = e < lon_E[j] && dx * dx + dy * dy <= reach2;
+            const uint32_t word = (__ballot_sync(kFull, near) >> sub_shift) & sub_mask;
+            if (jo == 0 && e < e_pad) {
+              masks[j * e_pad + e] = word;
+              if (word) pairs[atomicAdd(npairs, 1u)] = ((uint32_t)j << 16) | (uint32_t)e;
+            }
+          }
+        }
+      } else {
+        for (int e = warp; e < e_pad; e += wpc) {
+          const int row = obs_row0 + e * obs_row_step;
+          const bool in_tab = a.E_stage > 0 ? e < a.E_stage : row < a.T_obs;
+          const int m = e * res;
+          for (int j = 0; j < nv; ++j) {
+            const bool live = in_tab && e < lon_E[j];
+            const double fx = live ? PX[j * n_pad + m] : 0.0, fy = live ? PY[j * n_pad + m] : 0.0;
+            uint32_t any = 0u;
+            for (int w = 0; w < words; ++w) {
+              const int jo = w * 32 + lane;
+              bool near = false;
+              if (live) {
+                const double* slot = obs + row * (4 * Mp) + jo;
+                const double reach = reach0 + oc[2 * Mp + jo] * (1.0 + 1.0e-9);
+                const double dx = slot[0] - fx, dy = slot[Mp] - fy;
+                near = dx * dx + dy * dy <= reach * reach;
+              }
+              const uint32_t ball = __ballot_sync(kFull, near);
+              if (lane == 0) masks[(j * e_pad + e) * words + w] = ball;
+              any |= ball;
+            }
+            if (lane == 0 && any) pairs[atomicAdd(npairs, 1u)] = ((uint32_t)j << 16) | (uint32_t)e;
+          }
+        }
+      }
+    }
+    __syncthreads();
+
+    // ---- stage B, collision (has_collision, frenet_optimal_planner.py:168-195): one lane per
+    // (lateral row, listed (row, step) pair); exact predicate on the listed obstacles only
+    {
+      const uint32_t n_pairs = *npairs;
+      for (int ii = warp; ii < rows_i; ii += wpc) {
+        const double* Dr = lat + ii * n_pad;
+        for (uint32_t q = lane; q < n_pairs; q += 32) {
+          const uint32_t pr = pairs[q];
+          const int j = (int)(pr >> 16), e = (int)(pr & 0xffffu);
+          const double* pX = PX + j * n_pad;
+          const double* pY = PY + j * n_pad;
+          const double* uX = UX + j * n_pad;
+          const double* uY = UY + j * n_pad;
+          // ego pose at checked step i = e*check_res: centre (x_i, y_i), heading of segment min(i, n'-2)
+          const int i = e * res;
+          const int seg = min(i, lon_ncart[j] - 2);
+          double xa, ya, xb, yb;
+          grid_pos(pX, pY, uX, uY, Dr, seg, xa, ya);
+          grid_pos(pX, pY, uX, uY, Dr, seg + 1, xb, yb);
+          const double dxs = xb - xa, dys = yb - ya;
+          const double h2 = dxs * dxs + dys * dys;
+          double c, s;
+          if (h2 > 0.0 && h2 < 1.0e300) {
+            const double r = rsqrt(h2);  // cos/sin of atan2(dy, dx) without the round trip
+            c = dxs * r;
+            s = dys * r;
+          } else {
+            sincos(atan2(dys, dxs), &s, &c);
+          }
+          const double ex = i == seg ? xa : xb, ey = i == seg ? ya : yb;
+          const double* orow = obs + (obs_row0 + e * obs_row_step) * (4 * Mp);
+          const uint32_t* mw = masks + (j * e_pad + e) * words;
+          bool h = false;
+          for (int w = 0; w < words && !h; ++w) {
+            uint32_t bits = mw[w];
+            while (bits && !h) {
+              const int jo = w * 32 + __ffs(bits) - 1;
+              bits &= bits - 1;
+              const double* slot = orow + jo;
+              const double dx = slot[0] - ex, dy = slot[Mp] - ey;
+              const double thr = re + oc[2 * Mp + jo];
+              if (dx * dx + dy * dy <= thr * thr)
+                h = rect_sat(dx, dy, c, s, hle, hwe, slot[2 * Mp], slot[3 * Mp], oc[jo], oc[Mp + jo]);
+            }
+          }
+          if (h) atomicOr(&cflags[ii * nv + j], FISS_FLAG_COLLISION);
+        }
+      }
+    }
+
+    // ---- stage B, materialisation: one warp per candidate, lanes = time steps.  Heading / ds / curvature
+    // (:121-134) and the five output rows
+    if (kYaw) {
+      const int64_t id_base = (int64_t)b * a.C + (int64_t)i0 * a.sd + (int64_t)k * a.st;
+      for (int cidx = warp; cidx < n_cand; cidx += wpc) {
+        const int ii = (int)(((uint32_t)cidx * nv_magic) >> 20);
+        const int j = cidx - ii * nv;
+        const double* pX = PX + j * n_pad;
+        const double* pY = PY + j * n_pad;
+        const double* uX = UX + j * n_pad;
+        const double* uY = UY + j * n_pad;
+        const double* sD = SD + j * n_pad;
+        const double* Dr = lat + ii * n_pad;
+        const int n_cart = lon_ncart[j];
+        double* mx = a.mat ? a.mat + (id_base + ii * a.sd + j * a.sv) * a.n_stride : nullptr;  // row FISS_MAT_X
+        const int n_loop = a.mat ? a.n_stride : n_cart;
+        const bool has2 = n_cart >= 2;
+        unsigned curv = 0;
+        double carry = CUDART_NAN;  // yaw of the first step of the next (higher) 32-step block
+        for (int pass = (n_loop + 31) / 32 - 1; pass >= 0; --pass) {
+          const int m = pass * 32 + lane;
+          const bool in_cart = m < n_cart;
+          double xv = CUDART_NAN, yv = CUDART_NAN, yaw = CUDART_NAN, dx = 0.0, dy = 0.0, inv_ds = 0.0;
+          bool fast = false;
+          if (in_cart) {
+            if (has2) {
+              // yaw_m = atan2(dy, dx) of segment m for m < n'-1; the last point repeats the previous heading (:127-130)
+              const int seg = min(m, n_cart - 2);
+              double xa, ya, xb, yb;
+              grid_pos(pX, pY, uX, uY, Dr, seg, xa, ya);
+              grid_pos(pX, pY, uX, uY, Dr, seg + 1, xb, yb);
+              dx = xb - xa;
+              dy = yb - ya;
+              fast = segment_fast(dx, dy, yaw, inv_ds);
+              if (!fast) yaw = atan2(dy, dx);  // zero-length / non-finite segment: the library's special cases
+              xv = m == seg ? xa : xb;
+              yv = m == seg ? ya : yb;
+            } else {
+              grid_pos(pX, pY, uX, uY, Dr, m, xv, yv);  // n' == 1: the reference leaves yaw/ds/c empty (:121)
+            }
+          }
+          double yaw_next = __shfl_down_sync(kFull, yaw, 1);
+          if (lane == 31) yaw_next = carry;
+          carry = __shfl_sync(kFull, yaw, 0);
+          double kap = CUDART_NAN;
+          if (has2 && m < n_cart - 1) {
+            // c = dyaw / ds with ds = hypot(dx, dy) (:128,132; no unwrap; the last element is 0/ds)
+            kap = fast ? (yaw_next - yaw) * inv_ds : (yaw_next - yaw) / hypot(dx, dy);
+            if (p.check_curvature && fabs(kap) > p.max_curvature) curv = FISS_FLAG_CURVATURE;
+          }
+          if (mx && m < a.n_stride) {
+            mx[m] = xv;
+            mx[row_pitch + m] = yv;
+            mx[2 * row_pitch + m] = yaw;
+            mx[3 * row_pitch + m] = m < n ? sD[m] : CUDART_NAN;
+            mx[4 * row_pitch + m] = kap;
+          }
+        }
+        if (p.check_curvature) {
+          curv = warp_or(curv);
+          if (lane == 0 && curv) atomicOr(&cflags[cidx], curv);
+        }
+      }
+    }
+    __syncthreads();
+
+    // ---- stage C: one lane per candidate -- cost (cost_function.py:41-50) and the flags word
+    {
+      const int64_t id_base = (int64_t)b * a.C + (int64_t)i0 * a.sd + (int64_t)k * a.st;
+      const double inv_n = 1.0 / (double)n;
+      const double cost_time = p.cost_time_offset - (n - 1) * p.tick_t;  // (10 - t_last), cost_function.py:42
+      for (int cidx = threadIdx.x; cidx < n_cand; cidx += blockDim.x) {
+        const int ii = (int)(((uint32_t)cidx * nv_magic) >> 20);
+        const int j = cidx - ii * nv;
+        const int n_cart = lon_ncart[j];
+        const unsigned viol = lon_viol[j];
+        unsigned extra = cflags[cidx];
+        // n' == 1 with obstacles: traj.yaw[0] raises inside the try => "collision" (:178-182)
+        if (a.M > 0 && min(n_cart, t_left) > 0 && n_cart < 2 && (p.collide_all || viol == 0)) extra |= FISS_FLAG_COLLISION;
+        const int64_t out_id = id_base + ii * a.sd + j * a.sv;
+        a.cost[out_id] = (cost_time + (lon_cost[j] + lat_cost[ii])) * inv_n;
+        a.flags[out_id] = viol | extra | ((uint32_t)n_cart << FISS_FLAG_NCART_SHIFT);
+      }
+    }
+  }
+}
+
+}  // namespace fiss

@@ -45,8 +45,8 @@ struct EvalArgs {
   const double* spline;
   int32_t K, Kp, search_iters;
   // obstacle tables in global memory
-  const double* obs_tab;    // [T_obs][Mp][4] = (cx, cy, cos, sin)
-  const double* obs_const;  // [Mp][4] = (half_l, half_w, radius, 0)
+  const double* obs_tab;    // [T_obs][4][Mp]: rows cx, cy, cos, sin of every obstacle at one time step
+  const double* obs_const;  // [4][Mp]: rows half_l, half_w, circumscribed radius, 0
   int32_t M, Mp, mp_shift, T_obs, final_time_step;
   int32_t E_max;            // checked steps staged per CTA
   int32_t obs_in_smem;
@@ -293,21 +293,18 @@ __device__ __forceinline__ void eval_candidate(const EvalArgs& a, const double* 
         const int j = lane & (Mp - 1);
         const int e_off = lane >> a.mp_shift;
         const int spi = 32 >> a.mp_shift;  // checked steps per iteration
-        const double hlo = oc[4 * j], hwo = oc[4 * j + 1];
-        const double thr = re + oc[4 * j + 2];
+        const double hlo = oc[j], hwo = oc[Mp + j];
+        const double thr = re + oc[2 * Mp + j];
         const double thr2 = thr * thr;
         for (int e0 = 0; e0 < E; e0 += spi) {
           const int e = e0 + e_off;
           bool h = false;
           const int row = row0 + e * row_step;
           if (e < E && (a.obs_in_smem || row < a.T_obs)) {
-            const double* slot = obs + ((int64_t)row * Mp + j) * 4;
-            const double2 oxy = *reinterpret_cast<const double2*>(slot);
-            const double dx = oxy.x - ex[e], dy = oxy.y - ey[e];
-            if (dx * dx + dy * dy <= thr2) {
-              const double2 ocs = *reinterpret_cast<const double2*>(slot + 2);
-              h = rect_sat(dx, dy, ec[e], es[e], hle, hwe, ocs.x, ocs.y, hlo, hwo);
-            }
+            const double* slot = obs + (int64_t)row * 4 * Mp + j;  // conflict-free: lanes read consecutive doubles
+            const double dx = slot[0] - ex[e], dy = slot[Mp] - ey[e];
+            if (dx * dx + dy * dy <= thr2)
+              h = rect_sat(dx, dy, ec[e], es[e], hle, hwe, slot[2 * Mp], slot[3 * Mp], hlo, hwo);
           }
           if (__any_sync(kFull, h)) {
             hit = true;
@@ -321,14 +318,11 @@ __device__ __forceinline__ void eval_candidate(const EvalArgs& a, const double* 
           const int row = row0 + e * row_step;
           if (!a.obs_in_smem && row >= a.T_obs) break;  // past the predictions: no obstacle has a state
           for (int j = lane; j < Mp; j += 32) {
-            const double* slot = obs + ((int64_t)row * Mp + j) * 4;
-            const double2 oxy = *reinterpret_cast<const double2*>(slot);
-            const double dx = oxy.x - x, dy = oxy.y - y;
-            const double thr = re + oc[4 * j + 2];
-            if (dx * dx + dy * dy <= thr * thr) {
-              const double2 ocs = *reinterpret_cast<const double2*>(slot + 2);
-              h = h || rect_sat(dx, dy, c, s, hle, hwe, ocs.x, ocs.y, oc[4 * j], oc[4 * j + 1]);
-            }
+            const double* slot = obs + (int64_t)row * 4 * Mp + j;
+            const double dx = slot[0] - x, dy = slot[Mp] - y;
+            const double thr = re + oc[2 * Mp + j];
+            if (dx * dx + dy * dy <= thr * thr)
+              h = h || rect_sat(dx, dy, c, s, hle, hwe, slot[2 * Mp], slot[3 * Mp], oc[j], oc[Mp + j]);
           }
           hit = __any_sync(kFull, h);
         }
@@ -394,7 +388,7 @@ __device__ __forceinline__ void eval_candidate(const EvalArgs& a, const double* 
 
 // ------------------------------------------------------------------------------------------------
 // Shared-memory layout of the persistent CTA (doubles, after a 16-byte mbarrier slot):
-//   spline [9][Kp] | obstacle consts [Mp][4] | obstacle rows [E_max][Mp][4] (if obs_in_smem) |
+//   spline [9][Kp] | obstacle consts [4][Mp] | obstacle rows [E_max][4][Mp] (if obs_in_smem) |
 //   per-warp scratch [kWarpsPerCta][3 * n_pad + 4 * e_cap]
 __host__ __device__ inline int64_t scratch_doubles_per_warp(int n_pad, int e_cap) {
   return 3 * (int64_t)n_pad + 4 * (int64_t)e_cap;
@@ -438,7 +432,7 @@ __global__ void __launch_bounds__(kThreads) fiss_eval_kernel(const EvalArgs a) {
   // rows past the end of the predictions: nobody has a state there (state_at_time -> None)
   if (a.obs_in_smem) {
     for (int64_t q = (int64_t)rows_live * a.Mp * 4 + threadIdx.x; q < obs_doubles; q += blockDim.x)
-      obs_s[q] = ((q & 3) < 2) ? kObsFar : 0.0;
+      obs_s[q] = (((q / a.Mp) & 3) < 2) ? kObsFar : 0.0;
   }
   mbar_wait(bar, 0);
   __syncthreads();
@@ -549,37 +543,63 @@ __global__ void fiss_meta_kernel(const int32_t* __restrict__ best_idx, const dou
 }
 
 // ------------------------------------------------------------------------------------------------
-// Obstacle table preparation (once per scene): AoS host layout -> time-major device rows.
+// Obstacle table preparation (once per scene): AoS host layout -> time-major, component-planar rows.
 //   in : xyth [M][T][3], lw [M][2], valid [M][T]
-//   out: tab [T][Mp][4] = (cx, cy, cos th, sin th) with (kObsFar, kObsFar, 0, 0) where there is no state,
-//        oc  [Mp][4]    = (l/2, w/2, circumscribed radius, 0)
-__global__ void fiss_obstacle_prep_kernel(const double* __restrict__ xyth, const double* __restrict__ lw,
-                                          const uint8_t* __restrict__ valid, int M, int Mp, int T,
-                                          double* __restrict__ tab, double* __restrict__ oc) {
-  const int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+//   out: tab [T][4][Mp] = rows cx, cy, cos th, sin th, with (kObsFar, kObsFar, 0, 0) where there is no state
+//        oc  [4][Mp]    = rows l/2, w/2, circumscribed radius, 0
+// One time step is one contiguous 32*Mp-byte row (one bulk-TMA copy), and a warp whose lanes are
+// obstacles reads consecutive doubles of a component (no shared-memory bank conflicts).
+__device__ __forceinline__ void obstacle_store(double* __restrict__ tab, double* __restrict__ oc, int Mp, int T,
+                                               int64_t q, bool present, double x, double y, double th, double l,
+                                               double w) {
   if (q < Mp) {
     const int j = (int)q;
-    const double hl = j < M ? 0.5 * lw[2 * j] : 0.0;
-    const double hw = j < M ? 0.5 * lw[2 * j + 1] : 0.0;
-    oc[4 * j] = hl;
-    oc[4 * j + 1] = hw;
-    oc[4 * j + 2] = sqrt(hl * hl + hw * hw);
-    oc[4 * j + 3] = 0.0;
+    const double hl = 0.5 * l, hw = 0.5 * w;
+    oc[j] = hl;
+    oc[Mp + j] = hw;
+    oc[2 * Mp + j] = sqrt(hl * hl + hw * hw);
+    oc[3 * Mp + j] = 0.0;
   }
   if (q >= (int64_t)T * Mp) return;
   const int t = (int)(q / Mp);
   const int j = (int)(q - (int64_t)t * Mp);
-  double4 o = make_double4(kObsFar, kObsFar, 0.0, 0.0);
-  if (j < M && valid[(int64_t)j * T + t]) {
-    const double* s = xyth + ((int64_t)j * T + t) * 3;
-    double sn, cs;
-    sincos(s[2], &sn, &cs);
+  double cx = kObsFar, cy = kObsFar, cs = 0.0, sn = 0.0;
+  if (present) {
+    sincos(th, &sn, &cs);
     // shapely.affinity.rotate snaps |cos|, |sin| < 2.5e-16 to 0
     if (fabs(cs) < 2.5e-16) cs = 0.0;
     if (fabs(sn) < 2.5e-16) sn = 0.0;
-    o = make_double4(s[0], s[1], cs, sn);
+    cx = x;
+    cy = y;
   }
-  *reinterpret_cast<double4*>(tab + q * 4) = o;
+  double* row = tab + (int64_t)t * 4 * Mp + j;
+  row[0] = cx;
+  row[Mp] = cy;
+  row[2 * Mp] = cs;
+  row[3 * Mp] = sn;
+}
+
+__global__ void fiss_obstacle_prep_kernel(const double* __restrict__ xyth, const double* __restrict__ lw,
+                                          const uint8_t* __restrict__ valid, int M, int Mp, int T,
+                                          double* __restrict__ tab, double* __restrict__ oc) {
+  const int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int jc = (int)(q < Mp ? q : 0);
+  const double l = (q < Mp && jc < M) ? lw[2 * jc] : 0.0;
+  const double w = (q < Mp && jc < M) ? lw[2 * jc + 1] : 0.0;
+  bool present = false;
+  double x = 0.0, y = 0.0, th = 0.0;
+  if (q < (int64_t)T * Mp) {
+    const int t = (int)(q / Mp);
+    const int j = (int)(q - (int64_t)t * Mp);
+    if (j < M && valid[(int64_t)j * T + t]) {
+      const double* s = xyth + ((int64_t)j * T + t) * 3;
+      present = true;
+      x = s[0];
+      y = s[1];
+      th = s[2];
+    }
+  }
+  obstacle_store(tab, oc, Mp, T, q, present, x, y, th, l, w);
 }
 
 // Waymo wire format (waymo_interface.py:24-76): float32 [N][T][11] + mask [N][T] -> the same rows.
@@ -589,32 +609,27 @@ __global__ void fiss_obstacle_prep_waymo_kernel(const float* __restrict__ trajs,
                                                 int N, int Mp, int T, double* __restrict__ tab,
                                                 double* __restrict__ oc) {
   const int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (q < Mp) {
-    const int j = (int)q;
-    const double hl = j < N ? 0.5 * (double)trajs[((int64_t)j * T) * 11 + 3] : 0.0;
-    const double hw = j < N ? 0.5 * (double)trajs[((int64_t)j * T) * 11 + 4] : 0.0;
-    oc[4 * j] = hl;
-    oc[4 * j + 1] = hw;
-    oc[4 * j + 2] = sqrt(hl * hl + hw * hw);
-    oc[4 * j + 3] = 0.0;
-  }
-  if (q >= (int64_t)T * Mp) return;
-  const int t = (int)(q / Mp);
-  const int j = (int)(q - (int64_t)t * Mp);
-  double4 o = make_double4(kObsFar, kObsFar, 0.0, 0.0);
-  if (j < N) {
-    bool ok = true;
-    for (int u = 1; u <= t; ++u) ok = ok && mask[(int64_t)j * T + u] != 0;
-    if (ok) {
-      const float* s = trajs + ((int64_t)j * T + t) * 11;
-      double sn, cs;
-      sincos((double)s[6], &sn, &cs);
-      if (fabs(cs) < 2.5e-16) cs = 0.0;
-      if (fabs(sn) < 2.5e-16) sn = 0.0;
-      o = make_double4((double)s[0], (double)s[1], cs, sn);
+  const int jc = (int)(q < Mp ? q : 0);
+  const double l = (q < Mp && jc < N) ? (double)trajs[((int64_t)jc * T) * 11 + 3] : 0.0;
+  const double w = (q < Mp && jc < N) ? (double)trajs[((int64_t)jc * T) * 11 + 4] : 0.0;
+  bool present = false;
+  double x = 0.0, y = 0.0, th = 0.0;
+  if (q < (int64_t)T * Mp) {
+    const int t = (int)(q / Mp);
+    const int j = (int)(q - (int64_t)t * Mp);
+    if (j < N) {
+      bool ok = true;
+      for (int u = 1; u <= t; ++u) ok = ok && mask[(int64_t)j * T + u] != 0;
+      if (ok) {
+        const float* s = trajs + ((int64_t)j * T + t) * 11;
+        present = true;
+        x = (double)s[0];
+        y = (double)s[1];
+        th = (double)s[6];
+      }
     }
   }
-  *reinterpret_cast<double4*>(tab + q * 4) = o;
+  obstacle_store(tab, oc, Mp, T, q, present, x, y, th, l, w);
 }
 
 }  // namespace fiss

@@ -12,7 +12,7 @@ import ctypes as C
 import numpy as np
 
 from fiss_plus_planner_b200 import _shim
-from fiss_plus_planner_b200._shim import FissError, FissParams
+from fiss_plus_planner_b200._shim import FissError, FissGrid, FissParams
 
 
 def end_state_table(d, v, T, tick: float) -> np.ndarray:
@@ -20,6 +20,69 @@ def end_state_table(d, v, T, tick: float) -> np.ndarray:
     d, v, T = np.broadcast_arrays(np.asarray(d, np.float64), np.asarray(v, np.float64), np.asarray(T, np.float64))
     n = np.array([_shim.arange_len(t, tick) for t in T.ravel()], dtype=np.float64)
     return np.ascontiguousarray(np.column_stack((d.ravel(), v.ravel(), T.ravel(), n)))
+
+
+class LatticeGrid(object):
+    """A product lattice ``d_end x v_end x T`` plus its candidate numbering (``struct fiss_grid``).
+
+    ``order`` names the loop nest that numbers the candidates, outermost first: ``"dtv"`` is
+    FrenetOptimalPlanner's (frenet_optimal_planner.py:75,78,89), ``"dvt"`` FissPlanner's grid
+    ``[i_d][j_v][k_t]`` (fiss_planner.py:48,60,70)."""
+
+    def __init__(self, d, v, T, tick: float, order: str = "dtv"):
+        self.d = np.ascontiguousarray(d, dtype=np.float64)
+        self.v = np.ascontiguousarray(v, dtype=np.float64)
+        self.T = np.ascontiguousarray(T, dtype=np.float64)
+        assert sorted(order) == ["d", "t", "v"], order
+        self.order = order
+        self.tick = float(tick)
+        size = {"d": len(self.d), "v": len(self.v), "t": len(self.T)}
+        stride, acc = {}, 1
+        for ax in reversed(order):
+            stride[ax] = acc
+            acc *= size[ax]
+        self.strides = (stride["d"], stride["v"], stride["t"])
+        self.n = np.array([_shim.arange_len(t, tick) for t in self.T], dtype=np.int64)
+        self.num_candidates = acc
+        self.n_stride = int(self.n.max())
+        self._table = None
+        dp = C.POINTER(C.c_double)
+        self.c_struct = FissGrid(self.d.ctypes.data_as(dp), self.v.ctypes.data_as(dp), self.T.ctypes.data_as(dp),
+                                 len(self.d), len(self.v), len(self.T), *self.strides)
+
+    @property
+    def shape(self):
+        return len(self.d), len(self.v), len(self.T)
+
+    def index3(self, c):
+        """flat candidate id -> (i_d, j_v, k_t)."""
+        c = np.asarray(c)
+        sd, sv, st = self.strides
+        return (c // sd) % len(self.d), (c // sv) % len(self.v), (c // st) % len(self.T)
+
+    def table(self) -> np.ndarray:
+        """The expanded ``[C, 4] = (d_end, v_end, T, n)`` end-state table in candidate order."""
+        if self._table is None:
+            i, j, k = self.index3(np.arange(self.num_candidates))
+            self._table = np.ascontiguousarray(np.column_stack((self.d[i], self.v[j], self.T[k],
+                                                                self.n[k].astype(np.float64))))
+        return self._table
+
+
+def fop_grid(settings, vehicle_w: float) -> LatticeGrid:
+    """FrenetOptimalPlanner's lattice (frenet_optimal_planner.py:72-78,89) as a ``LatticeGrid``."""
+    sw = settings.max_road_width - vehicle_w
+    return LatticeGrid(np.linspace(-sw / 2, sw / 2, settings.num_width),
+                       np.linspace(settings.lowest_speed, settings.highest_speed, settings.num_speed),
+                       np.linspace(settings.min_t, settings.max_t, settings.num_t), settings.tick_t, "dtv")
+
+
+def fiss_grid(settings, vehicle_w: float) -> LatticeGrid:
+    """FissPlanner's lattice (fiss_planner.py:40-70: width + 0.3, grid [i_d][j_v][k_t])."""
+    sw = settings.max_road_width - vehicle_w + 0.3
+    return LatticeGrid(np.linspace(-sw / 2, sw / 2, settings.num_width),
+                       np.linspace(settings.lowest_speed, settings.highest_speed, settings.num_speed),
+                       np.linspace(settings.min_t, settings.max_t, settings.num_t), settings.tick_t, "dvt")
 
 
 def fop_lattice(settings, vehicle_w: float) -> np.ndarray:
@@ -150,6 +213,24 @@ class FissEngine:
             "fiss_plan_lattice_host")
         return dict(best_idx=best_idx, best_cost=best_cost, meta=meta, records=records, cost=cost, flags=flags)
 
+    def plan_grid(self, ego: np.ndarray, grid: LatticeGrid, params: FissParams, want_records: bool = True,
+                  want_volume: bool = False, stream=None) -> dict:
+        """plan() for ``ego [B, 6]`` over a product lattice (the lattice kernel)."""
+        ego = np.ascontiguousarray(np.atleast_2d(ego), dtype=np.float64)
+        b, c = ego.shape[0], grid.num_candidates
+        n_stride = grid.n_stride
+        best_idx = np.empty(b, np.int32)
+        best_cost = np.empty(b, np.float64)
+        meta = np.empty((b, 2), np.int32)
+        records = np.empty((b, _shim.REC_ROWS, n_stride), np.float64) if want_records else None
+        cost = np.empty((b, c), np.float64) if want_volume else None
+        flags = np.empty((b, c), np.uint32) if want_volume else None
+        self._check(self._lib.fiss_plan_grid_host(
+            self._h, self._stream(stream), _shim.ptr(ego), b, C.byref(grid.c_struct), C.byref(params),
+            _shim.ptr(best_idx), _shim.ptr(best_cost), _shim.ptr(meta), _shim.ptr(records), n_stride,
+            _shim.ptr(cost), _shim.ptr(flags)), "fiss_plan_grid_host")
+        return dict(best_idx=best_idx, best_cost=best_cost, meta=meta, records=records, cost=cost, flags=flags)
+
     def eval_end_states(self, ego6: np.ndarray, end: np.ndarray, params: FissParams, want_records: bool = False,
                         stream=None) -> dict:
         ego6 = np.ascontiguousarray(ego6, dtype=np.float64).reshape(6)
@@ -171,6 +252,13 @@ class FissEngine:
             self._h, self._stream(stream), C.c_void_p(ego_t.data_ptr()), b, C.c_void_p(end_t.data_ptr()), c,
             C.byref(params), C.c_void_p(cost_t.data_ptr()), C.c_void_p(flags_t.data_ptr()),
             C.c_void_p(mat_t.data_ptr()) if mat_t is not None else None, int(n_stride)), "fiss_eval_candidates_dev")
+
+    def eval_grid_dev(self, ego_t, grid: LatticeGrid, params: FissParams, cost_t, flags_t, mat_t, n_stride: int,
+                      stream=None):
+        self._check(self._lib.fiss_eval_grid_dev(
+            self._h, self._stream(stream), C.c_void_p(ego_t.data_ptr()), ego_t.shape[0], C.byref(grid.c_struct),
+            C.byref(params), C.c_void_p(cost_t.data_ptr()), C.c_void_p(flags_t.data_ptr()),
+            C.c_void_p(mat_t.data_ptr()) if mat_t is not None else None, int(n_stride)), "fiss_eval_grid_dev")
 
     def pick_winners_dev(self, ego_t, end_t, params: FissParams, cost_t, flags_t, best_idx_t, best_cost_t,
                          records_t, meta_t, n_stride: int, stream=None):

@@ -74,6 +74,23 @@ typedef struct fiss_params {
   int32_t collide_all;     /* 0: collision only for constraint survivors (plan(), :257-259); 1: for every candidate */
 } fiss_params;
 
+/* The product lattice the FOP / FOP+ / FISS planners sample: every (d_end[i], v_end[j], T[k]).
+ * Candidate c = i*stride_d + j*stride_v + k*stride_t, a dense numbering of [0, nd*nv*nt):
+ *   FrenetOptimalPlanner order (d outer, T, v inner; frenet_optimal_planner.py:75,78,89):
+ *       stride_d = nt*nv, stride_t = nv, stride_v = 1
+ *   FissPlanner grid [i_d][j_v][k_t] (fiss_planner.py:48,60,70):
+ *       stride_d = nv*nt, stride_v = nt, stride_t = 1
+ * The three axis arrays are HOST pointers (<= FISS_GRID_AXIS_MAX entries each); the step count of
+ * horizon T[k] is fiss_arange_len(T[k], tick_t). */
+#define FISS_GRID_AXIS_MAX 64
+typedef struct fiss_grid {
+  const double* d_end;
+  const double* v_end;
+  const double* T;
+  int32_t nd, nv, nt;
+  int32_t stride_d, stride_v, stride_t;
+} fiss_grid;
+
 /* ---- lifetime / errors ------------------------------------------------------------------- */
 int32_t fiss_create(int32_t device, fiss_handle** out);
 int32_t fiss_destroy(fiss_handle* h);
@@ -117,6 +134,17 @@ int32_t fiss_eval_candidates_dev(fiss_handle* h, void* stream, const double* d_e
                                  const double* d_end, int32_t C, const fiss_params* p,
                                  double* d_cost, uint32_t* d_flags, double* d_mat, int32_t n_stride);
 
+/* The same outputs for a product lattice, by the lattice kernel (csrc/fiss_grid_kernel.cuh): the
+ * work shared between candidates -- the longitudinal polynomial, spline frame, masks and cost terms
+ * per (v_end, T); the lateral polynomial and cost terms per (d_end, T); obstacle proximity per
+ * (v_end, T, step) -- is computed once per ego state in shared memory, then one warp per candidate
+ * does the Frenet->Cartesian conversion, heading/curvature, collision predicate and the stores.
+ * This is what FrenetOptimalPlanner.plan() (:247-270) launches.  Same d_cost / d_flags / d_mat
+ * layout and numbering as fiss_eval_candidates_dev with the expanded [C][4] table. */
+int32_t fiss_eval_grid_dev(fiss_handle* h, void* stream, const double* d_ego, int32_t B, const fiss_grid* g,
+                           const fiss_params* p, double* d_cost, uint32_t* d_flags, double* d_mat,
+                           int32_t n_stride);
+
 /* argmin with the reference's tie rule (:263-268: `min_cost >= cost` => last minimum wins) over the
  * feasible candidates of each problem, then the winner's full record.
  *   d_best_idx [B] (-1 when nothing survives), d_best_cost [B],
@@ -144,6 +172,11 @@ int32_t fiss_plan_lattice_host(fiss_handle* h, void* stream, const double* ego, 
                                const double* end, int32_t C, const fiss_params* p,
                                int32_t* best_idx, double* best_cost, int32_t* best_meta,
                                double* records, int32_t n_stride, double* cost, uint32_t* flags);
+
+/* plan() over a product lattice: fiss_eval_grid_dev + the pick + the winners' records, host buffers. */
+int32_t fiss_plan_grid_host(fiss_handle* h, void* stream, const double* ego, int32_t B, const fiss_grid* g,
+                            const fiss_params* p, int32_t* best_idx, double* best_cost, int32_t* best_meta,
+                            double* records, int32_t n_stride, double* cost, uint32_t* flags);
 
 /* "evaluate a list of end states" for one ego state: cost + masks for every entry,
  * and full records when `records` != NULL.  */

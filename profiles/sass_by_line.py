@@ -119,12 +119,14 @@ def main():
     for (f, ln), ex in by_line.most_common(args.top):
         print(f"{ex / div:12.1f} {100 * ex / total:5.1f}% {100 * by_line_stall[(f, ln)] / samples:5.1f}%  {f}:{ln}  {src(f, ln)}")
     if args.ranges:
-        print("# named ranges (fiss_kernels.cuh lines)")
+        print("# named ranges (name:[file:]lo-hi; default file fiss_kernels.cuh)")
         for item in args.ranges.split(","):
-            name, rng = item.split(":")
+            parts = item.split(":")
+            name, rng = parts[0], parts[-1]
+            fname = parts[1] if len(parts) == 3 else "fiss_kernels.cuh"
             lo, hi = [int(v) for v in rng.split("-")]
-            ex = sum(v for (f, ln), v in by_line.items() if f == "fiss_kernels.cuh" and lo <= ln <= hi)
-            st = sum(v for (f, ln), v in by_line_stall.items() if f == "fiss_kernels.cuh" and lo <= ln <= hi)
+            ex = sum(v for (f, ln), v in by_line.items() if f == fname and lo <= ln <= hi)
+            st = sum(v for (f, ln), v in by_line_stall.items() if f == fname and lo <= ln <= hi)
             print(f"{name:>12}: {ex / div:12.1f}{unit} {100 * ex / total:5.1f}% of instr, {100 * st / samples:5.1f}% of samples")
     print("# by opcode")
     for op, ex in by_op.most_common(25):
