@@ -63,6 +63,7 @@ struct PinBuf {
 
 constexpr size_t kSmemLimit = 227 * 1024;      // opt-in maximum per CTA on sm_100
 constexpr size_t kSmemObsBudget = 100 * 1024;  // stage obstacle rows only while 2 CTAs/SM still fit
+constexpr size_t kSmemCtaBudget = (228 * 1024) / fiss::kGridMinCtas - 1024;  // lattice kernel: kGridMinCtas CTAs/SM (1 KB/CTA is reserved)
 
 }  // namespace
 
@@ -239,9 +240,9 @@ int32_t ensure_grid(fiss_handle* h, cudaStream_t st, const fiss_grid* g, const f
   return FISS_OK;
 }
 
-template <bool kYaw>
+template <bool kYaw, bool kContig>
 int32_t launch_grid(fiss_handle* h, cudaStream_t st, const fiss::GridArgs& a, size_t smem, int threads, int which) {
-  auto kern = fiss::fiss_grid_kernel<kYaw>;
+  auto kern = fiss::fiss_grid_kernel<kYaw, kContig>;
   if (smem > h->smem_attr[which]) {
     FISS_CUDA(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemLimit));
     h->smem_attr[which] = kSmemLimit;
@@ -294,18 +295,29 @@ int32_t eval_grid(fiss_handle* h, cudaStream_t st, const double* d_ego, int B, c
   // obstacle rows of the checked steps go to shared memory while the CTA stays under the budget
   const int horizon = std::max(0, std::min(n_max, h->final_time_step - p->time_step_now));
   const int E_max = h->M > 0 ? (horizon + p->check_res - 1) / p->check_res : 0;
-  a.E_stage = E_max;
-  fiss::GridLayout L = fiss::grid_layout(a.Kp, a.Mp, a.E_stage, a.nv, a.d_chunk, a.n_pad, a.e_pad, a.words);
-  if (L.bytes > kSmemObsBudget && a.E_stage > 0) {
-    fiss::GridLayout L0 = fiss::grid_layout(a.Kp, a.Mp, 0, a.nv, a.d_chunk, a.n_pad, a.e_pad, a.words);
-    if (L.bytes > kSmemLimit || L0.bytes + (size_t)E_max * a.Mp * 32 > kSmemLimit) {
-      a.E_stage = 0;
-      L = L0;
+  // preference order: rows + transposed centres in shared memory; transposed centres only (the rare exact
+  // tests read the rows from L2); neither (ballot path of stage A' on global rows)
+  fiss::GridLayout L{};
+  const int tries[3][2] = {{E_max, E_max}, {0, E_max}, {0, 0}};
+  for (int t = 0; t < 3; ++t) {
+    a.E_stage = tries[t][0];
+    a.E_ot = tries[t][1];
+    L = fiss::grid_layout(a.Kp, a.Mp, a.E_stage, a.E_ot, a.nv, a.d_chunk, a.n_pad, a.e_pad, a.words);
+    if (L.bytes <= kSmemCtaBudget) break;
+  }
+  if (L.bytes > kSmemLimit) {  // over budget in every variant: take the first one that fits at all
+    for (int t = 0; t < 3; ++t) {
+      a.E_stage = tries[t][0];
+      a.E_ot = tries[t][1];
+      L = fiss::grid_layout(a.Kp, a.Mp, a.E_stage, a.E_ot, a.nv, a.d_chunk, a.n_pad, a.e_pad, a.words);
+      if (L.bytes <= kSmemLimit) break;
     }
   }
   if (L.bytes > kSmemLimit) return fail(h, FISS_ERR_CAPACITY, "lattice row tables exceed 227 KB of shared memory");
   const bool yaw = d_mat != nullptr || p->check_curvature;
-  return yaw ? launch_grid<true>(h, st, a, L.bytes, warps * 32, 4) : launch_grid<false>(h, st, a, L.bytes, warps * 32, 3);
+  if (!yaw) return launch_grid<false, false>(h, st, a, L.bytes, warps * 32, 3);
+  return a.sv == 1 ? launch_grid<true, true>(h, st, a, L.bytes, warps * 32, 4)
+                   : launch_grid<true, false>(h, st, a, L.bytes, warps * 32, 5);
 }
 
 }  // namespace

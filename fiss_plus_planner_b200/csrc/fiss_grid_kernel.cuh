@@ -61,6 +61,7 @@ struct GridArgs {
   const double* obs_const;  // [4][Mp]
   int32_t M, Mp, mp_shift, T_obs, final_time_step;
   int32_t E_stage;     // obstacle rows staged in shared memory (0: read them from global/L2)
+  int32_t E_ot;        // checked steps in the transposed centre table (0: ballot path of stage A')
   int32_t words;       // 32-bit mask words per (row, step) = max(1, Mp/32)
   int32_t n_pad;       // table row length (>= max n + 1, even)
   int32_t e_pad;       // mask row length (>= max checked steps)
@@ -72,18 +73,19 @@ struct GridArgs {
 
 // Shared-memory carve-up (byte offsets, 16-byte aligned), used by the host for the launch size too.
 struct GridLayout {
-  uint32_t spline, oc, obs, axes, lon, lat, lon_cost, lat_cost, dmax, lon_viol, lon_ncart, lon_E, npairs, pairs, cflags, masks, bytes;
+  uint32_t spline, oc, obs, ot, axes, lon, lat, lon_cost, lat_cost, dmax, lon_viol, lon_ncart, lon_E, npairs, pairs, cflags, masks, bytes;
 };
 
 __host__ __device__ inline uint32_t grid_align16(uint32_t v) { return (v + 15u) & ~15u; }
 
-__host__ __device__ inline GridLayout grid_layout(int Kp, int Mp, int E_stage, int nv, int d_chunk, int n_pad,
-                                                  int e_pad, int words) {
+__host__ __device__ inline GridLayout grid_layout(int Kp, int Mp, int E_stage, int E_ot, int nv, int d_chunk,
+                                                  int n_pad, int e_pad, int words) {
   GridLayout L;
   uint32_t o = 16;  // two mbarriers
   L.spline = o;     o += 9u * Kp * 8u;
   L.oc = o;         o += 4u * Mp * 8u;
   L.obs = o;        o += (uint32_t)E_stage * 4u * Mp * 8u;
+  L.ot = o;         o += (uint32_t)E_ot * 2u * Mp * 8u;
   L.axes = o;       o += 4u * kAxisMax * 8u;
   L.lon = o;        o += 5u * nv * n_pad * 8u;
   L.lat = o;        o += (uint32_t)d_chunk * n_pad * 8u;
@@ -111,14 +113,17 @@ __device__ __forceinline__ void grid_pos(const double* __restrict__ PX, const do
   y = PY[m] + d * UX[m];
 }
 
-template <bool kYaw>
+// kYaw: heading / curvature are needed (materialisation and/or the optional curvature mask).
+// kContig: v_end is the fastest-numbered axis (stride_v == 1), see stage B.
+template <bool kYaw, bool kContig>
 __global__ void __launch_bounds__(kGridThreads, kGridMinCtas) fiss_grid_kernel(const GridArgs a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  const GridLayout L = grid_layout(a.Kp, a.Mp, a.E_stage, a.nv, a.d_chunk, a.n_pad, a.e_pad, a.words);
+  const GridLayout L = grid_layout(a.Kp, a.Mp, a.E_stage, a.E_ot, a.nv, a.d_chunk, a.n_pad, a.e_pad, a.words);
   uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw);  // [0] spline, [1] obstacles
   double* sp = reinterpret_cast<double*>(smem_raw + L.spline);
   double* oc = reinterpret_cast<double*>(smem_raw + L.oc);
   double* obs_s = reinterpret_cast<double*>(smem_raw + L.obs);
+  double* ot = reinterpret_cast<double*>(smem_raw + L.ot);  // [2][Mp][E_ot]: obstacle centres, step-minor
   double* ax = reinterpret_cast<double*>(smem_raw + L.axes);
   double* lon = reinterpret_cast<double*>(smem_raw + L.lon);
   double* lat = reinterpret_cast<double*>(smem_raw + L.lat);
@@ -172,11 +177,21 @@ __global__ void __launch_bounds__(kGridThreads, kGridMinCtas) fiss_grid_kernel(c
     obs_s[q] = (((q / Mp) & 3) < 2) ? kObsFar : 0.0;
   for (int q = threadIdx.x; q < 4 * kAxisMax; q += blockDim.x) ax[q] = a.axes[q];
   mbar_wait(&bar[0], 0);
-  bool obstacles_ready = false;
+  mbar_wait(&bar[1], 0);
+  __syncthreads();
 
   const double* obs = a.E_stage > 0 ? obs_s : a.obs_tab;
   const int obs_row0 = a.E_stage > 0 ? 0 : p.time_step_now;
   const int obs_row_step = a.E_stage > 0 ? 1 : p.check_res;
+  // transposed centres OT[c][jo][e] (lanes that are consecutive checked steps read consecutive doubles)
+  for (int q = threadIdx.x; q < a.E_ot * Mp; q += blockDim.x) {
+    const int e = q / Mp, jo = q - e * Mp;
+    const int row = obs_row0 + e * obs_row_step;
+    const bool in_tab = a.E_stage > 0 ? e < a.E_stage : row < a.T_obs;
+    const double* slot = obs + row * (4 * Mp) + jo;
+    ot[jo * a.E_ot + e] = in_tab ? slot[0] : kObsFar;
+    ot[(Mp + jo) * a.E_ot + e] = in_tab ? slot[Mp] : kObsFar;
+  }
   const double hle = 0.5 * p.ego_length, hwe = 0.5 * p.ego_width;
   const double re = sqrt(hle * hle + hwe * hwe);
 
@@ -302,13 +317,37 @@ __global__ void __launch_bounds__(kGridThreads, kGridMinCtas) fiss_grid_kernel(c
     // ---- stage A': proximity masks.  Lanes = obstacles; a warp takes checked steps, keeps the obstacle
     // centres of that step in registers and walks the longitudinal rows: one ballot per (row, step).
     if (a.M > 0) {
-      if (!obstacles_ready) {
-        mbar_wait(&bar[1], 0);
-        obstacles_ready = true;
-      }
       const double dmax = __longlong_as_double((long long)*dmax_bits);
       const double reach0 = (dmax + re) * (1.0 + 1.0e-9) + 1.0e-9;
-      if (Mp <= 32) {
+      if (a.E_ot > 0) {
+        // one LANE per (row, checked step): walk the obstacles, build the mask words in registers
+        const uint32_t ep_magic = (1u << 20) / (uint32_t)e_pad + 1u;
+        for (int q = threadIdx.x; q < nv * e_pad; q += blockDim.x) {
+          const int j = (int)(((uint32_t)q * ep_magic) >> 20);
+          const int e = q - j * e_pad;
+          const bool live = e < lon_E[j] && e < a.E_ot;
+          uint32_t any = 0u;
+          if (live) {
+            const double fx = PX[j * n_pad + e * res], fy = PY[j * n_pad + e * res];
+            const double* ox = ot + e;
+            const double* oy = ot + Mp * a.E_ot + e;
+            for (int w = 0; w < words; ++w) {
+              uint32_t bits = 0u;
+              const int jo_end = min(a.M, w * 32 + 32);
+              for (int jo = w * 32; jo < jo_end; ++jo) {
+                const double dx = ox[jo * a.E_ot] - fx, dy = oy[jo * a.E_ot] - fy;
+                const double reach = reach0 + oc[2 * Mp + jo] * (1.0 + 1.0e-9);
+                if (dx * dx + dy * dy <= reach * reach) bits |= 1u << (jo & 31);
+              }
+              masks[q * words + w] = bits;
+              any |= bits;
+            }
+          } else {
+            for (int w = 0; w < words; ++w) masks[q * words + w] = 0u;
+          }
+          if (any) pairs[atomicAdd(npairs, 1u)] = ((uint32_t)j << 16) | (uint32_t)e;
+        }
+      } else if (Mp <= 32) {
         const int jo = lane & (Mp - 1);
         const int sub = lane >> a.mp_shift;
         const int ppi = 32 >> a.mp_shift;  // checked steps per warp iteration
@@ -366,9 +405,13 @@ __global__ void __launch_bounds__(kGridThreads, kGridMinCtas) fiss_grid_kernel(c
     // (lateral row, listed (row, step) pair); exact predicate on the listed obstacles only
     {
       const uint32_t n_pairs = *npairs;
-      for (int ii = warp; ii < rows_i; ii += wpc) {
-        const double* Dr = lat + ii * n_pad;
-        for (uint32_t q = lane; q < n_pairs; q += 32) {
+      const uint32_t n_work = (uint32_t)rows_i * n_pairs;
+      const uint32_t np_magic = n_pairs ? 0xffffffffu / n_pairs + 1u : 0u;  // w / n_pairs == umulhi(w, magic), w < 2^32 / n_pairs
+      for (uint32_t wk = threadIdx.x; wk < n_work; wk += blockDim.x) {
+        {
+          const int ii = n_pairs == 1u ? (int)wk : (int)__umulhi(wk, np_magic);
+          const uint32_t q = wk - (uint32_t)ii * n_pairs;
+          const double* Dr = lat + ii * n_pad;
           const uint32_t pr = pairs[q];
           const int j = (int)(pr >> 16), e = (int)(pr & 0xffffu);
           const double* pX = PX + j * n_pad;
@@ -412,67 +455,77 @@ __global__ void __launch_bounds__(kGridThreads, kGridMinCtas) fiss_grid_kernel(c
       }
     }
 
-    // ---- stage B, materialisation: one warp per candidate, lanes = time steps.  Heading / ds / curvature
-    // (:121-134) and the five output rows
+    // ---- stage B, materialisation: lanes = flattened (candidate, time step) elements.
+    // When v_end is the fastest-numbered axis (FrenetOptimalPlanner order) the nv candidates of one lateral row
+    // have consecutive ids, i.e. their output rows are one contiguous run of nv*n_stride doubles (a "group");
+    // otherwise a group is a single candidate.  A group is cut into blocks of 31 output elements: the 32nd
+    // lane of a block only supplies the heading of the next step (kappa_m needs yaw_{m+1}), so blocks are
+    // independent and are dealt round-robin to the warps of the CTA.  Heading / ds / curvature as
+    // frenet_optimal_planner.py:121-134.
     if (kYaw) {
-      const int64_t id_base = (int64_t)b * a.C + (int64_t)i0 * a.sd + (int64_t)k * a.st;
-      for (int cidx = warp; cidx < n_cand; cidx += wpc) {
-        const int ii = (int)(((uint32_t)cidx * nv_magic) >> 20);
-        const int j = cidx - ii * nv;
-        const double* pX = PX + j * n_pad;
-        const double* pY = PY + j * n_pad;
-        const double* uX = UX + j * n_pad;
-        const double* uY = UY + j * n_pad;
-        const double* sD = SD + j * n_pad;
+      const int G = kContig ? nv : 1;          // candidates per group
+      const int n_groups = kContig ? rows_i : n_cand;
+      const int ns = a.n_stride;
+      const uint32_t ns_magic = (1u << 20) / (uint32_t)ns + 1u;  // f / ns for f < 2^20 / ns
+      const int f_end = G * ns;
+      const int blocks_per_group = (f_end + 30) / 31;
+      const uint32_t bpg_magic = (1u << 20) / (uint32_t)blocks_per_group + 1u;
+      // element offset of candidate (i0, j = 0, k) in a materialised row; groups follow at group_pitch
+      double* const mat_item = a.mat ? a.mat + ((int64_t)b * a.C + (int64_t)i0 * a.sd + (int64_t)k * a.st) * ns : nullptr;
+      const int64_t lat_pitch = (int64_t)a.sd * ns, lon_pitch = (int64_t)a.sv * ns;
+      for (int task = warp; task < n_groups * blocks_per_group; task += wpc) {
+        const int g = (int)(((uint32_t)task * bpg_magic) >> 20);
+        const int f = (task - g * blocks_per_group) * 31 + lane;
+        int ii, j, m;
+        if (kContig) {
+          ii = g;
+          j = min((int)(((uint32_t)f * ns_magic) >> 20), nv - 1);
+          m = f - j * ns;  // >= ns for the lanes past the end of the group
+        } else {
+          ii = (int)(((uint32_t)g * nv_magic) >> 20);
+          j = g - ii * nv;
+          m = f;
+        }
+        const int tb = j * n_pad;
         const double* Dr = lat + ii * n_pad;
         const int n_cart = lon_ncart[j];
-        double* mx = a.mat ? a.mat + (id_base + ii * a.sd + j * a.sv) * a.n_stride : nullptr;  // row FISS_MAT_X
-        const int n_loop = a.mat ? a.n_stride : n_cart;
-        const bool has2 = n_cart >= 2;
-        unsigned curv = 0;
-        double carry = CUDART_NAN;  // yaw of the first step of the next (higher) 32-step block
-        for (int pass = (n_loop + 31) / 32 - 1; pass >= 0; --pass) {
-          const int m = pass * 32 + lane;
-          const bool in_cart = m < n_cart;
-          double xv = CUDART_NAN, yv = CUDART_NAN, yaw = CUDART_NAN, dx = 0.0, dy = 0.0, inv_ds = 0.0;
-          bool fast = false;
-          if (in_cart) {
-            if (has2) {
-              // yaw_m = atan2(dy, dx) of segment m for m < n'-1; the last point repeats the previous heading (:127-130)
-              const int seg = min(m, n_cart - 2);
-              double xa, ya, xb, yb;
-              grid_pos(pX, pY, uX, uY, Dr, seg, xa, ya);
-              grid_pos(pX, pY, uX, uY, Dr, seg + 1, xb, yb);
-              dx = xb - xa;
-              dy = yb - ya;
-              fast = segment_fast(dx, dy, yaw, inv_ds);
-              if (!fast) yaw = atan2(dy, dx);  // zero-length / non-finite segment: the library's special cases
-              xv = m == seg ? xa : xb;
-              yv = m == seg ? ya : yb;
-            } else {
-              grid_pos(pX, pY, uX, uY, Dr, m, xv, yv);  // n' == 1: the reference leaves yaw/ds/c empty (:121)
-            }
-          }
-          double yaw_next = __shfl_down_sync(kFull, yaw, 1);
-          if (lane == 31) yaw_next = carry;
-          carry = __shfl_sync(kFull, yaw, 0);
-          double kap = CUDART_NAN;
-          if (has2 && m < n_cart - 1) {
-            // c = dyaw / ds with ds = hypot(dx, dy) (:128,132; no unwrap; the last element is 0/ds)
-            kap = fast ? (yaw_next - yaw) * inv_ds : (yaw_next - yaw) / hypot(dx, dy);
-            if (p.check_curvature && fabs(kap) > p.max_curvature) curv = FISS_FLAG_CURVATURE;
-          }
-          if (mx && m < a.n_stride) {
-            mx[m] = xv;
-            mx[row_pitch + m] = yv;
-            mx[2 * row_pitch + m] = yaw;
-            mx[3 * row_pitch + m] = m < n ? sD[m] : CUDART_NAN;
-            mx[4 * row_pitch + m] = kap;
+        const bool in_cart = m < n_cart;  // (n' <= n <= ns)
+        double xv = CUDART_NAN, yv = CUDART_NAN, yaw = CUDART_NAN, dx = 0.0, dy = 0.0, inv_ds = 0.0;
+        bool fast = false;
+        if (in_cart) {
+          if (n_cart >= 2) {
+            // yaw_m = atan2(dy, dx) of segment m for m < n'-1; the last point repeats the previous heading (:127-130)
+            const int seg = min(m, n_cart - 2);
+            double xa, ya, xb, yb;
+            grid_pos(PX + tb, PY + tb, UX + tb, UY + tb, Dr, seg, xa, ya);
+            grid_pos(PX + tb, PY + tb, UX + tb, UY + tb, Dr, seg + 1, xb, yb);
+            dx = xb - xa;
+            dy = yb - ya;
+            fast = segment_fast(dx, dy, yaw, inv_ds);
+            if (!fast) yaw = atan2(dy, dx);  // zero-length / non-finite segment: the library's special cases
+            xv = m == seg ? xa : xb;
+            yv = m == seg ? ya : yb;
+          } else {
+            grid_pos(PX + tb, PY + tb, UX + tb, UY + tb, Dr, m, xv, yv);  // n' == 1: yaw/ds/c stay empty (:121)
           }
         }
-        if (p.check_curvature) {
-          curv = warp_or(curv);
-          if (lane == 0 && curv) atomicOr(&cflags[cidx], curv);
+        // the next step of the same candidate is the next lane; the last step of a candidate never looks at
+        // its neighbour (m >= n' - 1), and lane 31 writes nothing
+        const double yaw_next = __shfl_down_sync(kFull, yaw, 1);
+        double kap = CUDART_NAN;
+        if (m < n_cart - 1) {
+          // c = dyaw / ds with ds = hypot(dx, dy) (:128,132; no unwrap; the last element is 0/ds)
+          kap = fast ? (yaw_next - yaw) * inv_ds : (yaw_next - yaw) / hypot(dx, dy);
+          if (p.check_curvature && lane < 31 && fabs(kap) > p.max_curvature)
+            atomicOr(&cflags[ii * nv + j], FISS_FLAG_CURVATURE);
+        }
+        if (mat_item && lane < 31 && m < ns) {
+          double* o = mat_item + (ii * lat_pitch + j * lon_pitch + m);
+          o[0] = xv;
+          o[row_pitch] = yv;
+          o[2 * row_pitch] = yaw;
+          o[3 * row_pitch] = m < n ? SD[tb + m] : CUDART_NAN;
+          o[4 * row_pitch] = kap;
         }
       }
     }

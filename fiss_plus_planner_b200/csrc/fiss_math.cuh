@@ -12,29 +12,42 @@
 namespace fiss {
 
 // atan(q) = q + q^3 * P(q^2) on q in [0, 1]: Chebyshev-node interpolant of atan(sqrt(u))/sqrt(u), degree 19
-// in u (tools/fit_atan.py: max relative error of the float64 Horner evaluation 2.5e-16).
+// in u (tools/fit_atan.py: max relative error of the float64 Horner evaluation 2.5e-16).  kAtanP[k] multiplies
+// q^(2k+3).  In constant memory so that every FMA takes its coefficient as a constant-bank operand (literals
+// cost two uniform-register moves per coefficient).
+__constant__ double kAtanP[19] = {
+    -0.333333333333307,     0.1999999999964796,   -0.14285714266926733,  0.11111110578002083,
+    -0.09090899793217341,   0.07692198997458294,  -0.06665764910689723,  0.058768281144872724,
+    -0.052374234719188166,  0.04668745304848529,  -0.040811247503178855, 0.03387126702700675,
+    -0.02556862364437174,   0.01671959606350739,  -0.00899108054265826,  0.003751138483965141,
+    -0.0011252544302234645, 0.00021423810738603946, -1.93423475928923e-05};
+
 __device__ __forceinline__ double atan_unit(double q) {
+  // P(u) = E(w) + u * O(w) with w = u^2: two independent Horner chains, half the dependent-FMA latency
   const double u = q * q;
-  double p = -1.93423475928923e-05;
-  p = fma(p, u, 0.00021423810738603946);
-  p = fma(p, u, -0.0011252544302234645);
-  p = fma(p, u, 0.003751138483965141);
-  p = fma(p, u, -0.00899108054265826);
-  p = fma(p, u, 0.01671959606350739);
-  p = fma(p, u, -0.02556862364437174);
-  p = fma(p, u, 0.03387126702700675);
-  p = fma(p, u, -0.040811247503178855);
-  p = fma(p, u, 0.04668745304848529);
-  p = fma(p, u, -0.052374234719188166);
-  p = fma(p, u, 0.058768281144872724);
-  p = fma(p, u, -0.06665764910689723);
-  p = fma(p, u, 0.07692198997458294);
-  p = fma(p, u, -0.09090899793217341);
-  p = fma(p, u, 0.11111110578002083);
-  p = fma(p, u, -0.14285714266926733);
-  p = fma(p, u, 0.1999999999964796);
-  p = fma(p, u, -0.333333333333307);
-  return fma(q * u, p, q);
+  const double w = u * u;
+  double e = kAtanP[18];
+  double o = kAtanP[17];
+#pragma unroll
+  for (int k = 16; k >= 2; k -= 2) {
+    e = fma(e, w, kAtanP[k]);
+    o = fma(o, w, kAtanP[k - 1]);
+  }
+  e = fma(e, w, kAtanP[0]);
+  return fma(q * u, fma(u, o, e), q);
+}
+
+// mn / mx for 0 <= mn <= mx, mx in the normal range: reciprocal seed + two Newton steps + one residual
+// correction (the generic division's special-case handling is not needed here); <= 1 ulp.
+__device__ __forceinline__ double ratio_unit(double mn, double mx) {
+  double r;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(mx));
+  double e = fma(-mx, r, 1.0);
+  r = fma(r, e, r);
+  e = fma(-mx, r, 1.0);
+  r = fma(r, e, r);
+  const double q = mn * r;
+  return fma(r, fma(-mx, q, mn), q);
 }
 
 // atan2 for a finite, non-degenerate vector (max(|x|, |y|) in the normal range); ~3e-16 relative.
@@ -42,7 +55,7 @@ __device__ __forceinline__ double atan2_finite(double y, double x) {
   const double ax = fabs(x), ay = fabs(y);
   const bool steep = ay > ax;
   const double mx = steep ? ay : ax, mn = steep ? ax : ay;
-  double a = atan_unit(mn / mx);
+  double a = atan_unit(ratio_unit(mn, mx));
   if (steep) a = 1.5707963267948966 - a;
   if (x < 0.0) a = 3.141592653589793 - a;
   return copysign(a, y);

@@ -17,7 +17,7 @@ import heapq
 import numpy as np
 
 from fiss_plus_planner_b200 import _shim
-from fiss_plus_planner_b200.engine import fiss_lattice
+from fiss_plus_planner_b200.engine import fiss_grid, fiss_lattice
 from fiss_plus_planner_b200.planners.common.scenario.frenet import FrenetState, FrenetTrajectory
 from fiss_plus_planner_b200.planners.common.vehicle.vehicle import Vehicle
 from fiss_plus_planner_b200.planners.frenet_optimal_planner import (CandidateBundle, FrenetOptimalPlanner,
@@ -62,6 +62,7 @@ class FissPlanner(FrenetOptimalPlanner):
         self.trajs_per_timestep = []
         # device-computed volumes for the current cycle
         self._table = None
+        self._fgrid = None
         self._cost = None
         self._flags = None
         self._generated = None
@@ -80,6 +81,7 @@ class FissPlanner(FrenetOptimalPlanner):
         ``find_initial_guess`` sees the same ties."""
         st = self.settings
         table, ds, vs, ts, res = fiss_lattice(st, self.vehicle.w)
+        self._fgrid = fiss_grid(st, self.vehicle.w)      # same points, as axes + [i_d][j_v][k_t] numbering
         sw = st.max_road_width - self.vehicle.w + 0.3
         left, right = -sw / 2, sw / 2
         self.sampling_min[:] = (left, st.lowest_speed, st.min_t)
@@ -128,8 +130,8 @@ class FissPlanner(FrenetOptimalPlanner):
     def _evaluate_grid(self, time_step_now: int):
         """The one launch per cycle: cost + masks of every lattice point."""
         self._prm = self._params(time_step_now)
-        out = self.engine.eval_end_states(self._ego6, self._table, self._prm, want_records=False)
-        self._cost, self._flags = out["cost"], out["flags"]
+        out = self.engine.plan_grid(self._ego6[None], self._fgrid, self._prm, want_records=False, want_volume=True)
+        self._cost, self._flags = out["cost"][0], out["flags"][0]
 
     # -- lazy generation (bookkeeping only; the numbers are already on the host) ---------------------
     def generate_trajectory(self, idx: np.ndarray) -> tuple:

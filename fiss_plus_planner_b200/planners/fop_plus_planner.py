@@ -45,7 +45,7 @@ class FopPlusPlanner(FrenetOptimalPlanner):
         end = self._end_states()
         prm = self._params(time_step_now)
         ego6 = frenet_state.as_ego6()
-        out = self.engine.plan_lattice(ego6[None], end, prm, want_records=True, want_volume=True)
+        out = self.engine.plan_grid(ego6[None], self._lattice_grid(), prm, want_records=True, want_volume=True)
         cost, flags = out["cost"][0], out["flags"][0]
         self.stats.num_trajs_generated = len(end)
         self.all_trajs.append(CandidateBundle(self.engine, ego6, end, prm, cost, flags))

@@ -6,9 +6,9 @@ cubic_spline, best_traj, all_trajs, stats``) and methods (``generate_frenet_fram
 
 What differs is where the work happens.  The reference walks the (d, T, v) lattice in three nested
 Python loops and then runs calc_global_paths / check_constraints / check_collisions over Python
-lists.  Here ``plan()`` marshals six ego numbers, the end-state table and one ``fiss_params``
-struct, and ONE call into libfissgpu.so evaluates every candidate (one warp each), picks the
-winner with the reference's tie rule and returns the winner's arrays.  ``all_trajs`` stays
+lists.  Here ``plan()`` marshals six ego numbers, the lattice axes and one ``fiss_params`` struct,
+and ONE call into libfissgpu.so (``fiss_plan_grid_host``: the lattice kernel) evaluates every
+candidate, picks the winner with the reference's tie rule and returns the winner's arrays.  ``all_trajs`` stays
 populated (the GIF renderer reads it, planning.py:352-355) but lazily: a cycle's candidate bundle
 is only materialised on the device and copied back when somebody indexes it.
 """
@@ -19,7 +19,7 @@ import collections.abc
 import numpy as np
 
 from fiss_plus_planner_b200 import _shim
-from fiss_plus_planner_b200.engine import FissEngine, decode_flags, fop_lattice, make_params
+from fiss_plus_planner_b200.engine import FissEngine, decode_flags, fop_grid, make_params
 from fiss_plus_planner_b200.planners.common.cost.cost_function import CostFunction
 from fiss_plus_planner_b200.planners.common.geometry.cubic_spline import CubicSpline2D
 from fiss_plus_planner_b200.planners.common.scenario.frenet import FrenetState, FrenetTrajectory
@@ -172,6 +172,7 @@ class FrenetOptimalPlanner(object):
         self._obstacle_key = None
         self._lattice_key = None
         self._lattice = None
+        self._grid = None
         self.check_curvature = False  # optional third mask bit; off = reference behaviour (:145-150)
 
     # -- device plumbing -------------------------------------------------------------------------
@@ -198,9 +199,15 @@ class FrenetOptimalPlanner(object):
         key = (st.max_road_width, self.vehicle.w, st.num_width, st.min_t, st.max_t, st.num_t, st.lowest_speed,
                st.highest_speed, st.num_speed, st.tick_t)
         if key != self._lattice_key:
-            self._lattice = fop_lattice(st, self.vehicle.w)
+            self._grid = fop_grid(st, self.vehicle.w)
+            self._lattice = self._grid.table()
             self._lattice_key = key
         return self._lattice
+
+    def _lattice_grid(self):
+        """The same lattice as a ``LatticeGrid`` (axes + numbering) for the lattice kernel."""
+        self._end_states()
+        return self._grid
 
     def _params(self, time_step_now: int, collide_all: bool = False):
         return make_params(self.settings, self.vehicle, self.cost_function.as_device_weights(), time_step_now,
@@ -230,7 +237,7 @@ class FrenetOptimalPlanner(object):
         prm = self._params(time_step_now)
         ego6 = frenet_state.as_ego6() if hasattr(frenet_state, "as_ego6") else np.array(
             [frenet_state.s, frenet_state.s_d, frenet_state.s_dd, frenet_state.d, frenet_state.d_d, frenet_state.d_dd])
-        out = self.engine.plan_lattice(ego6[None], end, prm, want_records=True, want_volume=True)
+        out = self.engine.plan_grid(ego6[None], self._lattice_grid(), prm, want_records=True, want_volume=True)
 
         n_cand = len(end)
         self.stats.num_trajs_generated = n_cand

@@ -28,7 +28,12 @@ def ncu_sass(rep: str, launch: int):
     kernel = rows[0][1]
     hdr = rows[1]
     col = {n: i for i, n in enumerate(hdr)}
-    data = [r for r in rows[2:] if len(r) == len(hdr)]
+    data = []
+    for r in rows[2:]:
+        if r == hdr:  # the page repeats the listing; keep the first copy
+            break
+        if len(r) == len(hdr):
+            data.append(r)
     return kernel, col, data
 
 

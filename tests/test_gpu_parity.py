@@ -276,30 +276,35 @@ def test_grid_matches_generic_kernel(case):
         np.testing.assert_array_equal(a["meta"], r["meta"])
         np.testing.assert_array_equal(np.isnan(a["records"]), np.isnan(r["records"]))
 
+    # materialised rows, in FrenetOptimalPlanner numbering (v fastest: grouped stores) and in FissPlanner
+    # numbering (T fastest: one candidate per group)
+    from fiss_plus_planner_b200.engine import LatticeGrid
     dev = torch.device("cuda:0")
-    c, n_stride = grid.num_candidates, grid.n_stride
+    sptr = torch.cuda.current_stream().cuda_stream
     ego_t = torch.tensor(sc.ego, dtype=torch.float64, device=dev)
-    end_t = torch.tensor(end, dtype=torch.float64, device=dev)
-    outs = []
-    for which in ("grid", "generic"):
-        cost_t = torch.empty(b * c, dtype=torch.float64, device=dev)
-        flags_t = torch.empty(b * c, dtype=torch.int32, device=dev)
-        mat_t = torch.full((5, b * c, n_stride), 7.0, dtype=torch.float64, device=dev)
-        sptr = torch.cuda.current_stream().cuda_stream
-        if which == "grid":
-            eng.eval_grid_dev(ego_t, grid, prm, cost_t, flags_t, mat_t, n_stride, stream=sptr)
-        else:
-            eng.eval_candidates_dev(ego_t, end_t, prm, cost_t, flags_t, mat_t, n_stride, stream=sptr)
-        torch.cuda.synchronize()
-        outs.append((cost_t.cpu().numpy(), flags_t.cpu().numpy(), mat_t.cpu().numpy()))
-    (gc, gf, gm), (rc, rf, rm) = outs
-    np.testing.assert_array_equal(gf, rf)
-    np.testing.assert_allclose(gc, rc, rtol=1e-13)
-    np.testing.assert_array_equal(np.isnan(gm), np.isnan(rm))
-    # x, y agree to a few ulp (FMA contraction differs between the two kernels); yaw and kappa are finite
-    # differences of those over segments down to ~1e-3 m, hence the absolute terms
-    for row, (rtol, atol) in enumerate(((1e-13, 0), (1e-13, 0), (1e-9, ATOL_YAW), (1e-10, 1e-13), (1e-6, ATOL_KAPPA))):
-        np.testing.assert_allclose(gm[row], rm[row], rtol=rtol, atol=atol, err_msg=f"mat row {row}")
+    for order in ("dtv", "dvt"):
+        gr = grid if order == "dtv" else LatticeGrid(grid.d, grid.v, grid.T, st.tick_t, order)
+        c, n_stride = gr.num_candidates, gr.n_stride
+        end_t = torch.tensor(gr.table(), dtype=torch.float64, device=dev)
+        outs = []
+        for which in ("grid", "generic"):
+            cost_t = torch.empty(b * c, dtype=torch.float64, device=dev)
+            flags_t = torch.empty(b * c, dtype=torch.int32, device=dev)
+            mat_t = torch.full((5, b * c, n_stride), 7.0, dtype=torch.float64, device=dev)
+            if which == "grid":
+                eng.eval_grid_dev(ego_t, gr, prm, cost_t, flags_t, mat_t, n_stride, stream=sptr)
+            else:
+                eng.eval_candidates_dev(ego_t, end_t, prm, cost_t, flags_t, mat_t, n_stride, stream=sptr)
+            torch.cuda.synchronize()
+            outs.append((cost_t.cpu().numpy(), flags_t.cpu().numpy(), mat_t.cpu().numpy()))
+        (gc, gf, gm), (rc, rf, rm) = outs
+        np.testing.assert_array_equal(gf, rf)
+        np.testing.assert_allclose(gc, rc, rtol=1e-13)
+        np.testing.assert_array_equal(np.isnan(gm), np.isnan(rm))
+        # x, y agree to a few ulp (FMA contraction differs between the two kernels); yaw and kappa are finite
+        # differences of those over segments down to ~1e-3 m, hence the absolute terms
+        for row, (rtol, atol) in enumerate(((1e-13, 0), (1e-13, 0), (1e-9, ATOL_YAW), (1e-10, 1e-13), (1e-6, ATOL_KAPPA))):
+            np.testing.assert_allclose(gm[row], rm[row], rtol=rtol, atol=atol, err_msg=f"mat row {row} order {order}")
 
 
 def test_grid_rejects_bad_grids():
