@@ -103,3 +103,42 @@ def test_fop_returns_stale_best_when_nothing_survives():
     plp.vehicle.max_accel = 1e-3
     assert plp.plan(fs, float(g["max_target_speed"]), obs, 0) is None
     assert plp.stats.num_iter == 125
+
+
+def test_batch_front_end_single_rank_matches_engine():
+    """ShardedBatchPlanner / SplitLatticePlanner at world size 1 are the plain engine calls (the N > 1
+    reductions are covered on CPU by tests/test_multi_rank_gloo.py)."""
+    from fiss_plus_planner_b200 import synthetic as syn
+    from fiss_plus_planner_b200.batch import ShardedBatchPlanner, SplitLatticePlanner
+    from fiss_plus_planner_b200.engine import FissEngine, fop_grid, make_params
+    from fiss_plus_planner_b200.planners.common.cost.cost_function import CostFunction
+    from fiss_plus_planner_b200.planners.common.vehicle.vehicle import Vehicle
+    from fiss_plus_planner_b200.planners.frenet_optimal_planner import FrenetOptimalPlannerSettings
+    sc = syn.make_scene("cfg4_batch4096_32obs", batch=16)
+    veh = Vehicle(syn.vehicle_params())
+    st = FrenetOptimalPlannerSettings(*sc.num_samples)
+    st.min_t, st.max_t, st.highest_speed = sc.min_t, sc.max_t, sc.max_target_speed
+    eng = FissEngine(0)
+    eng.set_spline(sc.spline.device_table())
+    eng.set_obstacles(sc.obs.xyth, sc.obs.lw, sc.obs.valid, sc.obs.final_time_step)
+    grid = fop_grid(st, veh.w)
+    prm = make_params(st, veh, CostFunction("WX1").as_device_weights())
+    ref = eng.plan_grid(sc.ego, grid, prm, want_records=True)
+    loc = ShardedBatchPlanner(eng, grid, prm).plan_local(sc.ego)
+    assert loc["problems"] == (0, 16)
+    np.testing.assert_array_equal(loc["best_idx"], ref["best_idx"])
+    out = SplitLatticePlanner(eng, grid, prm).plan(sc.ego)
+    np.testing.assert_array_equal(out["best_idx"], ref["best_idx"])
+    np.testing.assert_array_equal(out["records"], ref["records"])
+    # the lattice split by hand into two slabs of lateral rows, picked with the reference's tie rule
+    from fiss_plus_planner_b200.engine import LatticeGrid
+    lo = LatticeGrid(grid.d[:5], grid.v, grid.T, grid.tick, "dtv")
+    hi = LatticeGrid(grid.d[5:], grid.v, grid.T, grid.tick, "dtv")
+    a, b = eng.plan_grid(sc.ego, lo, prm), eng.plan_grid(sc.ego, hi, prm)
+    off = 5 * grid.strides[0]
+    for p in range(16):
+        cands = [(a["best_cost"][p], int(a["best_idx"][p])) if a["best_idx"][p] >= 0 else None,
+                 (b["best_cost"][p], int(b["best_idx"][p]) + off) if b["best_idx"][p] >= 0 else None]
+        cands = [c for c in cands if c is not None]
+        want = max((c for c in cands if c[0] == min(x[0] for x in cands)), key=lambda c: c[1])[1] if cands else -1
+        assert want == int(ref["best_idx"][p])
