@@ -181,7 +181,7 @@ def run_ours(args):
     # CPU baseline first (rank 0, N=1 only), before CUDA is initialised in this process (fork-safe)
     cpu = None
     if n_gpus == 1 and not args.no_cpu_baseline:
-        cpu = cpu_port_rate(sc, steps=4, warmup=1, budget_s=40.0)
+        cpu = cpu_port_rate(sc, steps=args.cpu_steps, warmup=1, budget_s=40.0)
 
     from fiss_plus_planner_b200.engine import FissEngine, fop_grid, make_params
     from fiss_plus_planner_b200.planners.common.cost.cost_function import CostFunction
@@ -304,6 +304,12 @@ def run_ours(args):
         else:
             peak, peak_src = 6650.0, "fallback 6.65 TB/s (B200_PROFILING.md)"
         alg = algorithmic_bytes(end, B, NUM_OBS, len(sc.spline.s))
+        # DRAM bytes per launch of the same kernel / workload from the committed `ncu --set full` capture
+        traffic, traffic_src = None, None
+        tpath = os.path.join(ROOT, "profiles", "traffic.json")
+        if os.path.exists(tpath) and bpg == BATCH_PER_GPU:
+            tj = json.load(open(tpath))
+            traffic, traffic_src = tj["dram_bytes_per_launch"], tj["source"]
         achieved = alg / (kern_ms * 1e-3) / 1e9
         cand_total = B * C * n_gpus
         line = {
@@ -318,7 +324,8 @@ def run_ours(args):
                     "call": "fiss_plan_grid_host (host ego states in, winners + full records out)"},
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": None, "kernel": "fiss_grid_kernel<yaw> (materialising)", "kernel_ms": kern_ms,
+                         "traffic": traffic, "traffic_source": traffic_src,
+                         "kernel": "fiss_grid_kernel<yaw> (materialising)", "kernel_ms": kern_ms,
                          "algorithmic_bytes_per_launch": alg, "peak_source": peak_src,
                          "note": "FP64-issue bound by arithmetic (SURVEY 8(d)); see profiles/ for ncu fp64 pipe utilisation"},
             "plan_cycle_p50_ms": p50,
@@ -367,6 +374,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch-per-gpu", type=int, default=BATCH_PER_GPU)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-steps", type=int, default=150,
+                    help="CPU-baseline sample: lattices evaluated by the oracle port (150 x ~80 ms = ~12 s of host time)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":
