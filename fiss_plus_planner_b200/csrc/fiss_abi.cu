@@ -103,6 +103,19 @@ int32_t fail(fiss_handle* h, int32_t code, const std::string& msg) {
       return fail(h, FISS_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(e_));          \
   } while (0)
 
+// True when `p` is page-locked host memory known to the CUDA runtime (cudaHostAlloc / cudaHostRegister / a torch
+// pinned tensor): the *_host entry points then DMA straight from / into it instead of bouncing through the
+// handle's own pinned staging and a host memcpy.
+bool host_is_pinned(const void* p) {
+  if (!p) return false;
+  cudaPointerAttributes at;
+  if (cudaPointerGetAttributes(&at, p) != cudaSuccess) {
+    cudaGetLastError();
+    return false;
+  }
+  return at.type == cudaMemoryTypeHost;
+}
+
 int32_t check_params(fiss_handle* h, const fiss_params* p) {
   if (!p) return fail(h, FISS_ERR_INVALID, "params is NULL");
   if (!(p->tick_t > 0.0)) return fail(h, FISS_ERR_INVALID, "tick_t must be > 0");
@@ -594,15 +607,23 @@ static int32_t plan_common(fiss_handle* h, cudaStream_t st, const double* ego, i
   FISS_CUDA(h, h->d_best_cost.ensure((size_t)B * 8));
   FISS_CUDA(h, h->d_meta.ensure((size_t)B * 8));
   if (records) FISS_CUDA(h, h->d_records.ensure(rec_doubles * 8));
-  // pinned staging: [ego] in, [best_cost | records | cost | best_idx | meta | flags] out
-  FISS_CUDA(h, h->h_in.ensure((size_t)B * 48));
-  const size_t o_cost = 0, o_rec = o_cost + (size_t)B * 8, o_vol = o_rec + rec_doubles * 8,
-               o_idx = o_vol + (cost ? total * 8 : 0), o_meta = o_idx + (size_t)B * 4,
-               o_flags = o_meta + (size_t)B * 8, o_end = o_flags + (flags ? total * 4 : 0);
+  // pinned staging: [ego] in, [best_cost | records | cost | best_idx | meta | flags] out -- each piece only when
+  // the caller's own buffer is not page-locked (a pinned caller buffer is the DMA source / target itself)
+  const bool pin_ego = host_is_pinned(ego), pin_cost = host_is_pinned(best_cost), pin_idx = host_is_pinned(best_idx),
+             pin_meta = host_is_pinned(best_meta), pin_rec = host_is_pinned(records), pin_vol = host_is_pinned(cost),
+             pin_flags = host_is_pinned(flags);
+  const size_t o_cost = 0, o_rec = o_cost + (pin_cost ? 0 : (size_t)B * 8), o_vol = o_rec + (pin_rec ? 0 : rec_doubles * 8),
+               o_idx = o_vol + (cost && !pin_vol ? total * 8 : 0), o_meta = o_idx + (pin_idx ? 0 : (size_t)B * 4),
+               o_flags = o_meta + (pin_meta ? 0 : (size_t)B * 8), o_end = o_flags + (flags && !pin_flags ? total * 4 : 0);
   FISS_CUDA(h, h->h_out.ensure(o_end));
   char* ho = h->h_out.as<char>();
-  std::memcpy(h->h_in.p, ego, (size_t)B * 48);
-  FISS_CUDA(h, cudaMemcpyAsync(h->d_ego.p, h->h_in.p, (size_t)B * 48, cudaMemcpyHostToDevice, st));
+  const void* ego_src = ego;
+  if (!pin_ego) {
+    FISS_CUDA(h, h->h_in.ensure((size_t)B * 48));
+    std::memcpy(h->h_in.p, ego, (size_t)B * 48);
+    ego_src = h->h_in.p;
+  }
+  FISS_CUDA(h, cudaMemcpyAsync(h->d_ego.p, ego_src, (size_t)B * 48, cudaMemcpyHostToDevice, st));
   if (g) {
     rc = eval_grid(h, st, h->d_ego.as<double>(), B, g, n_max, p, h->d_cost.as<double>(), h->d_flags.as<uint32_t>(),
                    nullptr, n_stride);
@@ -616,19 +637,25 @@ static int32_t plan_common(fiss_handle* h, cudaStream_t st, const double* ego, i
                              h->d_best_cost.as<double>(), records ? h->d_records.as<double>() : nullptr,
                              h->d_meta.as<int32_t>(), n_stride);
   if (rc != FISS_OK) return rc;
-  FISS_CUDA(h, cudaMemcpyAsync(ho + o_cost, h->d_best_cost.p, (size_t)B * 8, cudaMemcpyDeviceToHost, st));
-  FISS_CUDA(h, cudaMemcpyAsync(ho + o_idx, h->d_best_idx.p, (size_t)B * 4, cudaMemcpyDeviceToHost, st));
-  FISS_CUDA(h, cudaMemcpyAsync(ho + o_meta, h->d_meta.p, (size_t)B * 8, cudaMemcpyDeviceToHost, st));
-  if (records) FISS_CUDA(h, cudaMemcpyAsync(ho + o_rec, h->d_records.p, rec_doubles * 8, cudaMemcpyDeviceToHost, st));
-  if (cost) FISS_CUDA(h, cudaMemcpyAsync(ho + o_vol, h->d_cost.p, total * 8, cudaMemcpyDeviceToHost, st));
-  if (flags) FISS_CUDA(h, cudaMemcpyAsync(ho + o_flags, h->d_flags.p, total * 4, cudaMemcpyDeviceToHost, st));
+  void* t_cost = pin_cost ? (void*)best_cost : (void*)(ho + o_cost);
+  void* t_idx = pin_idx ? (void*)best_idx : (void*)(ho + o_idx);
+  void* t_meta = pin_meta ? (void*)best_meta : (void*)(ho + o_meta);
+  void* t_rec = pin_rec ? (void*)records : (void*)(ho + o_rec);
+  void* t_vol = pin_vol ? (void*)cost : (void*)(ho + o_vol);
+  void* t_flags = pin_flags ? (void*)flags : (void*)(ho + o_flags);
+  FISS_CUDA(h, cudaMemcpyAsync(t_cost, h->d_best_cost.p, (size_t)B * 8, cudaMemcpyDeviceToHost, st));
+  FISS_CUDA(h, cudaMemcpyAsync(t_idx, h->d_best_idx.p, (size_t)B * 4, cudaMemcpyDeviceToHost, st));
+  FISS_CUDA(h, cudaMemcpyAsync(t_meta, h->d_meta.p, (size_t)B * 8, cudaMemcpyDeviceToHost, st));
+  if (records) FISS_CUDA(h, cudaMemcpyAsync(t_rec, h->d_records.p, rec_doubles * 8, cudaMemcpyDeviceToHost, st));
+  if (cost) FISS_CUDA(h, cudaMemcpyAsync(t_vol, h->d_cost.p, total * 8, cudaMemcpyDeviceToHost, st));
+  if (flags) FISS_CUDA(h, cudaMemcpyAsync(t_flags, h->d_flags.p, total * 4, cudaMemcpyDeviceToHost, st));
   FISS_CUDA(h, cudaStreamSynchronize(st));
-  std::memcpy(best_cost, ho + o_cost, (size_t)B * 8);
-  std::memcpy(best_idx, ho + o_idx, (size_t)B * 4);
-  if (best_meta) std::memcpy(best_meta, ho + o_meta, (size_t)B * 8);
-  if (records) std::memcpy(records, ho + o_rec, rec_doubles * 8);
-  if (cost) std::memcpy(cost, ho + o_vol, total * 8);
-  if (flags) std::memcpy(flags, ho + o_flags, total * 4);
+  if (!pin_cost) std::memcpy(best_cost, t_cost, (size_t)B * 8);
+  if (!pin_idx) std::memcpy(best_idx, t_idx, (size_t)B * 4);
+  if (best_meta && !pin_meta) std::memcpy(best_meta, t_meta, (size_t)B * 8);
+  if (records && !pin_rec) std::memcpy(records, t_rec, rec_doubles * 8);
+  if (cost && !pin_vol) std::memcpy(cost, t_vol, total * 8);
+  if (flags && !pin_flags) std::memcpy(flags, t_flags, total * 4);
   return FISS_OK;
 }
 

@@ -213,23 +213,44 @@ class FissEngine:
             "fiss_plan_lattice_host")
         return dict(best_idx=best_idx, best_cost=best_cost, meta=meta, records=records, cost=cost, flags=flags)
 
+    @staticmethod
+    def pinned_empty(shape, dtype) -> np.ndarray:
+        """Page-locked host array (a torch pinned tensor viewed as NumPy; the view keeps the tensor alive).  The
+        ``*_host`` entry points DMA straight from / into such arrays instead of staging + memcpy."""
+        import torch
+        tdt = {np.dtype(np.float64): torch.float64, np.dtype(np.int32): torch.int32, np.dtype(np.uint32): torch.int32}[np.dtype(dtype)]
+        arr = torch.empty(tuple(int(v) for v in np.atleast_1d(shape)), dtype=tdt, pin_memory=True).numpy()
+        return arr.view(dtype)
+
+    def alloc_plan_outputs(self, batch: int, grid: LatticeGrid, want_records: bool = True, want_volume: bool = False,
+                           pinned: bool = True) -> dict:
+        """Reusable output buffers for ``plan_grid(..., out=)``: winners, (n, n') and optionally the winners' full
+        records and the whole cost / flags volume."""
+        mk = self.pinned_empty if pinned else (lambda shape, dt: np.empty(shape, dt))
+        b, c, ns = int(batch), grid.num_candidates, grid.n_stride
+        return dict(best_idx=mk((b,), np.int32), best_cost=mk((b,), np.float64), meta=mk((b, 2), np.int32),
+                    records=mk((b, _shim.REC_ROWS, ns), np.float64) if want_records else None,
+                    cost=mk((b, c), np.float64) if want_volume else None,
+                    flags=mk((b, c), np.uint32) if want_volume else None)
+
     def plan_grid(self, ego: np.ndarray, grid: LatticeGrid, params: FissParams, want_records: bool = True,
-                  want_volume: bool = False, stream=None) -> dict:
-        """plan() for ``ego [B, 6]`` over a product lattice (the lattice kernel)."""
-        ego = np.ascontiguousarray(np.atleast_2d(ego), dtype=np.float64)
+                  want_volume: bool = False, stream=None, out: dict = None) -> dict:
+        """plan() for ``ego [B, 6]`` over a product lattice (the lattice kernel).  ``out`` (from
+        ``alloc_plan_outputs``) is filled in place and returned: no allocation on the call path, and pinned
+        buffers -- ``ego`` included -- are the DMA endpoints themselves."""
+        if not (isinstance(ego, np.ndarray) and ego.ndim == 2 and ego.dtype == np.float64 and ego.flags.c_contiguous):
+            ego = np.ascontiguousarray(np.atleast_2d(ego), dtype=np.float64)
         b, c = ego.shape[0], grid.num_candidates
         n_stride = grid.n_stride
-        best_idx = np.empty(b, np.int32)
-        best_cost = np.empty(b, np.float64)
-        meta = np.empty((b, 2), np.int32)
-        records = np.empty((b, _shim.REC_ROWS, n_stride), np.float64) if want_records else None
-        cost = np.empty((b, c), np.float64) if want_volume else None
-        flags = np.empty((b, c), np.uint32) if want_volume else None
+        if out is None:
+            out = self.alloc_plan_outputs(b, grid, want_records, want_volume, pinned=False)
+        else:
+            assert out["best_idx"].shape == (b,) and (out["records"] is None or out["records"].shape[2] == n_stride)
         self._check(self._lib.fiss_plan_grid_host(
             self._h, self._stream(stream), _shim.ptr(ego), b, C.byref(grid.c_struct), C.byref(params),
-            _shim.ptr(best_idx), _shim.ptr(best_cost), _shim.ptr(meta), _shim.ptr(records), n_stride,
-            _shim.ptr(cost), _shim.ptr(flags)), "fiss_plan_grid_host")
-        return dict(best_idx=best_idx, best_cost=best_cost, meta=meta, records=records, cost=cost, flags=flags)
+            _shim.ptr(out["best_idx"]), _shim.ptr(out["best_cost"]), _shim.ptr(out["meta"]), _shim.ptr(out["records"]),
+            n_stride, _shim.ptr(out["cost"]), _shim.ptr(out["flags"])), "fiss_plan_grid_host")
+        return out
 
     def eval_end_states(self, ego6: np.ndarray, end: np.ndarray, params: FissParams, want_records: bool = False,
                         stream=None) -> dict:

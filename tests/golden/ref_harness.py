@@ -150,3 +150,98 @@ def load_reference():
     from planners.common.geometry.polynomial import QuarticPolynomial, QuinticPolynomial
     from planners.common.cost.cost_function import CostFunction
     return types.SimpleNamespace(**{k: v for k, v in locals().items()})
+
+
+# --------------------------------------------------------------------------- closed-loop driver (planning.py)
+def install_driver_stubs():
+    """Stubs that let the reference's OWN ``planners/benchmark/planning.py`` and
+    ``planners/commonroad_interface/global_planner.py`` import and run unmodified:
+
+    * ``commonroad.*`` names they use resolve to the stand-ins of
+      ``fiss_plus_planner_b200/planners/commonroad_interface/commonroad_lite.py`` (scenario objects, ``CustomState``,
+      ``Trajectory``) -- commonroad-io itself is absent;
+    * ``commonroad_route_planner.route_planner.RoutePlanner`` resolves to the stand-in route search of our
+      ``global_planner.py`` (the reference's own concatenation / de-dup / heading code then runs on its result);
+    * matplotlib, PIL, omegaconf, commonroad_dc, SMP: inert modules (rendering / SMP are out of scope).
+    """
+    install_stubs()
+    import enum
+    from fiss_plus_planner_b200.planners.commonroad_interface import commonroad_lite as crl
+    from fiss_plus_planner_b200.planners.commonroad_interface import global_planner as gpl
+    from fiss_plus_planner_b200.planners.commonroad_interface import vehicle_parameters as vpar
+
+    class _Inert(types.ModuleType):
+        def __getattr__(self, name):
+            if name.startswith("__"):
+                raise AttributeError(name)
+            return type(name, (), {})
+
+    def mod(name, **attrs):
+        m = sys.modules.get(name)
+        if m is None or not isinstance(m, types.ModuleType):
+            m = _Inert(name)
+            sys.modules[name] = m
+        for k, v in attrs.items():
+            setattr(m, k, v)
+        parent, _, child = name.rpartition(".")
+        if parent:
+            setattr(mod(parent), child, m)
+        return m
+
+    for name in ("matplotlib", "matplotlib.pyplot", "matplotlib.collections", "PIL", "PIL.Image", "omegaconf",
+                 "commonroad.common", "commonroad.common.solution", "commonroad.geometry", "commonroad.geometry.shape",
+                 "commonroad.planning", "commonroad.planning.planning_problem", "commonroad.prediction",
+                 "commonroad.prediction.prediction", "commonroad.visualization", "commonroad.visualization.mp_renderer",
+                 "commonroad.scenario.traffic_sign", "commonroad.scenario.traffic_sign_interpreter",
+                 "commonroad_dc", "commonroad_dc.feasibility", "commonroad_dc.feasibility.vehicle_dynamics",
+                 "commonroad_route_planner", "commonroad_route_planner.utility",
+                 "commonroad_route_planner.utility.visualization",
+                 "SMP", "SMP.maneuver_automaton", "SMP.maneuver_automaton.maneuver_automaton", "SMP.motion_planner",
+                 "SMP.motion_planner.motion_planner", "SMP.motion_planner.utility"):
+        mod(name)
+    mod("PIL", Image=mod("PIL.Image"))
+    mod("commonroad.common.file_reader", CommonRoadFileReader=crl.CommonRoadFileReader)
+    mod("commonroad.scenario.state", CustomState=crl.CustomState)
+    mod("commonroad.scenario.trajectory", Trajectory=crl.Trajectory)
+    mod("commonroad.scenario.obstacle", DynamicObstacle=crl.DynamicObstacle, ObstacleType=type("ObstacleType", (), {"CAR": "car"}))
+    mod("commonroad.geometry.shape", Rectangle=crl.Rectangle)
+    mod("commonroad.prediction.prediction", TrajectoryPrediction=crl.TrajectoryPrediction)
+    mod("commonroad_dc.feasibility.vehicle_dynamics", VehicleParameterMapping=vpar.VehicleParameterMapping)
+    mod("commonroad.common.solution", VehicleType=vpar.VehicleType)
+
+    class RoutePlanner(gpl.RoutePlanner):
+        class Backend(enum.Enum):
+            NETWORKX = "networkx"
+            NETWORKX_REVERSED = "networkx_reversed"
+            PRIORITY_QUEUE = "priority_queue"
+
+        def __init__(self, scenario, planning_problem, backend=None):
+            super().__init__(scenario, planning_problem)
+
+    mod("commonroad_route_planner.route_planner", RoutePlanner=RoutePlanner)
+
+
+class RefRectangle:
+    """What the reference reads of an obstacle shape (:189): ``shapely_object`` -- here the stand-in polygon."""
+
+    def __init__(self, length, width):
+        self.length, self.width = length, width
+        hl, hw = length / 2.0, width / 2.0
+        self.shapely_object = Polygon([(-hl, -hw), (-hl, hw), (hl, hw), (hl, -hw), (-hl, -hw)])
+
+
+def load_reference_driver():
+    """Import the reference's planning.py (unmodified) and return its ``frenet_optimal_planning``."""
+    install_driver_stubs()
+    import importlib
+    planning = importlib.import_module("planners.benchmark.planning")
+    return planning
+
+
+def attach_shapely_shapes(scenario):
+    """Give every obstacle shape of a commonroad_lite scenario the ``shapely_object`` the reference reads."""
+    for ob in scenario.static_obstacles + scenario.dynamic_obstacles:
+        sh = ob.obstacle_shape
+        if not hasattr(sh, "shapely_object"):
+            sh.shapely_object = RefRectangle(sh.length, sh.width).shapely_object
+    return scenario
