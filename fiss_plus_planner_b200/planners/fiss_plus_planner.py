@@ -151,15 +151,27 @@ class FissPlusPlanner(FissPlanner):
         resolutions = self.sampling_res
         J_new = traj.cost_final
         x = np.array([traj.end_state.d, traj.end_state.s_d, traj.end_state.t])
+        x0 = np.array(x)
         for _ in range(self.settings.max_refine_iters):
             valid, J_new, x, resolutions = self.gradient_decent(J_new, x, resolutions, self.settings.decaying_factor)
             if not valid:
                 break
             if time.time() - t_start >= time_limit:
                 break
+        # Refined candidates are costed by the list kernel, the coarse winner by the lattice kernel: the two agree
+        # to ~1e-16, but the reference's `>` sees an EXACT tie whenever a clipped neighbour coincides with the coarse
+        # end state (x on the boundary of the sampling box) and then returns the refined copy (idx = [-1, -1, -1]).
+        # Near a tie, compare against the coarse end state costed by the same kernel as the candidates.
+        thr = traj.cost_final
+        thr_same_kernel = None
         while self.refined_trajs:
             cand = heapq.heappop(self.refined_trajs)
-            if cand.cost_final > traj.cost_final:
+            if abs(cand.cost_final - traj.cost_final) <= 1e-9 * abs(traj.cost_final):
+                if thr_same_kernel is None:
+                    row = end_state_table(x0[:1], x0[1:2], x0[2:3], self.settings.tick_t)
+                    thr_same_kernel = float(self.engine.eval_end_states(self._ego6, row, self._prm)["cost"][0])
+                thr = thr_same_kernel
+            if cand.cost_final > thr:
                 break
             if self._validate_flags(cand.flags):
                 out = self._fetch_trajectory(cand.row, cand.cost_final)
