@@ -253,9 +253,9 @@ int32_t ensure_grid(fiss_handle* h, cudaStream_t st, const fiss_grid* g, const f
   return FISS_OK;
 }
 
-template <bool kYaw, bool kContig>
+template <bool kYaw>
 int32_t launch_grid(fiss_handle* h, cudaStream_t st, const fiss::GridArgs& a, size_t smem, int threads, int which) {
-  auto kern = fiss::fiss_grid_kernel<kYaw, kContig>;
+  auto kern = fiss::fiss_grid_kernel<kYaw>;
   if (smem > h->smem_attr[which]) {
     FISS_CUDA(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemLimit));
     h->smem_attr[which] = kSmemLimit;
@@ -328,9 +328,7 @@ int32_t eval_grid(fiss_handle* h, cudaStream_t st, const double* d_ego, int B, c
   }
   if (L.bytes > kSmemLimit) return fail(h, FISS_ERR_CAPACITY, "lattice row tables exceed 227 KB of shared memory");
   const bool yaw = d_mat != nullptr || p->check_curvature;
-  if (!yaw) return launch_grid<false, false>(h, st, a, L.bytes, warps * 32, 3);
-  return a.sv == 1 ? launch_grid<true, true>(h, st, a, L.bytes, warps * 32, 4)
-                   : launch_grid<true, false>(h, st, a, L.bytes, warps * 32, 5);
+  return yaw ? launch_grid<true>(h, st, a, L.bytes, warps * 32, 4) : launch_grid<false>(h, st, a, L.bytes, warps * 32, 3);
 }
 
 }  // namespace

@@ -43,6 +43,10 @@ constexpr int kGridThreads = kGridWarps * 32;
 #endif
 constexpr int kGridMinCtas = FISS_GRID_MIN_CTAS;  // resident CTAs per SM the register budget is capped for
 constexpr int kAxisMax = 64;  // lattice points per axis
+#ifndef FISS_MAT_GROUP
+#define FISS_MAT_GROUP 3
+#endif
+constexpr int kMatRows = FISS_MAT_GROUP;  // lateral rows one materialisation task walks with the same frame points
 
 struct GridArgs {
   const double* ego;   // [B][6]
@@ -105,17 +109,17 @@ __host__ __device__ inline GridLayout grid_layout(int Kp, int Mp, int E_stage, i
 
 // Candidate position at step m from the row tables (same expression as the generic kernel:
 // x = px - d*(ty*r), y = py + d*(tx*r) with the unit tangent stored already multiplied out).
-__device__ __forceinline__ void grid_pos(const double* __restrict__ PX, const double* __restrict__ PY,
-                                         const double* __restrict__ UX, const double* __restrict__ UY,
+// P2[m] = (px, py) and U2[m] = (ux, uy) are 16-byte pairs: one LDS.128 each, conflict-free for consecutive m.
+__device__ __forceinline__ void grid_pos(const double2* __restrict__ P2, const double2* __restrict__ U2,
                                          const double* __restrict__ D, int m, double& x, double& y) {
+  const double2 P = P2[m], U = U2[m];
   const double d = D[m];
-  x = PX[m] - d * UY[m];
-  y = PY[m] + d * UX[m];
+  x = P.x - d * U.y;
+  y = P.y + d * U.x;
 }
 
 // kYaw: heading / curvature are needed (materialisation and/or the optional curvature mask).
-// kContig: v_end is the fastest-numbered axis (stride_v == 1), see stage B.
-template <bool kYaw, bool kContig>
+template <bool kYaw>
 __global__ void __launch_bounds__(kGridThreads, kGridMinCtas) fiss_grid_kernel(const GridArgs a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const GridLayout L = grid_layout(a.Kp, a.Mp, a.E_stage, a.E_ot, a.nv, a.d_chunk, a.n_pad, a.e_pad, a.words);
@@ -145,11 +149,9 @@ __global__ void __launch_bounds__(kGridThreads, kGridMinCtas) fiss_grid_kernel(c
   const int n_pad = a.n_pad;
   const int Mp = a.Mp;
   const int row_len = a.nv * n_pad;  // one longitudinal table
-  double* PX = lon;
-  double* PY = lon + row_len;
-  double* UX = lon + 2 * row_len;
-  double* UY = lon + 3 * row_len;
-  double* SD = lon + 4 * row_len;
+  double2* P2 = reinterpret_cast<double2*>(lon);                // [nv][n_pad] frame point (px, py)
+  double2* U2 = reinterpret_cast<double2*>(lon + 2 * row_len);  // [nv][n_pad] unit tangent (ux, uy)
+  double* SD = lon + 4 * row_len;                               // [nv][n_pad] longitudinal speed
 
   // ---- stage 0: tables.  The spline is needed first (stage A); the obstacle rows only in stage A'.
   if (threadIdx.x == 0) {
@@ -256,10 +258,8 @@ __global__ void __launch_bounds__(kGridThreads, kGridMinCtas) fiss_grid_kernel(c
           double px, py, tx, ty;
           if (spline_frame(sp, a.K, a.Kp, a.search_iters, s, px, py, tx, ty)) {
             const double r = rsqrt(tx * tx + ty * ty);
-            PX[base + m] = px;
-            PY[base + m] = py;
-            UX[base + m] = tx * r;
-            UY[base + m] = ty * r;
+            P2[base + m] = make_double2(px, py);
+            U2[base + m] = make_double2(tx * r, ty * r);
           } else {
             first_bad = min(first_bad, m);
           }
@@ -328,7 +328,8 @@ __global__ void __launch_bounds__(kGridThreads, kGridMinCtas) fiss_grid_kernel(c
           const bool live = e < lon_E[j] && e < a.E_ot;
           uint32_t any = 0u;
           if (live) {
-            const double fx = PX[j * n_pad + e * res], fy = PY[j * n_pad + e * res];
+            const double2 fp = P2[j * n_pad + e * res];
+            const double fx = fp.x, fy = fp.y;
             const double* ox = ot + e;
             const double* oy = ot + Mp * a.E_ot + e;
             for (int w = 0; w < words; ++w) {
@@ -363,7 +364,8 @@ __global__ void __launch_bounds__(kGridThreads, kGridMinCtas) fiss_grid_kernel(c
           const double ox = in_tab ? slot[0] : kObsFar, oy = in_tab ? slot[Mp] : kObsFar;
           const int m = min(e * res, n_pad - 1);
           for (int j = 0; j < nv; ++j) {
-            const double dx = ox - PX[j * n_pad + m], dy = oy - PY[j * n_pad + m];
+            const double2 fp = P2[j * n_pad + m];
+            const double dx = ox - fp.x, dy = oy - fp.y;
             const bool near = e < lon_E[j] && dx * dx + dy * dy <= reach2;
             const uint32_t word = (__ballot_sync(kFull, near) >> sub_shift) & sub_mask;
             if (jo == 0 && e < e_pad) {
@@ -379,7 +381,8 @@ __global__ void __launch_bounds__(kGridThreads, kGridMinCtas) fiss_grid_kernel(c
           const int m = e * res;
           for (int j = 0; j < nv; ++j) {
             const bool live = in_tab && e < lon_E[j];
-            const double fx = live ? PX[j * n_pad + m] : 0.0, fy = live ? PY[j * n_pad + m] : 0.0;
+            const double2 fp = live ? P2[j * n_pad + m] : make_double2(0.0, 0.0);
+            const double fx = fp.x, fy = fp.y;
             uint32_t any = 0u;
             for (int w = 0; w < words; ++w) {
               const int jo = w * 32 + lane;
@@ -414,16 +417,14 @@ __global__ void __launch_bounds__(kGridThreads, kGridMinCtas) fiss_grid_kernel(c
           const double* Dr = lat + ii * n_pad;
           const uint32_t pr = pairs[q];
           const int j = (int)(pr >> 16), e = (int)(pr & 0xffffu);
-          const double* pX = PX + j * n_pad;
-          const double* pY = PY + j * n_pad;
-          const double* uX = UX + j * n_pad;
-          const double* uY = UY + j * n_pad;
+          const double2* pP = P2 + j * n_pad;
+          const double2* pU = U2 + j * n_pad;
           // ego pose at checked step i = e*check_res: centre (x_i, y_i), heading of segment min(i, n'-2)
           const int i = e * res;
           const int seg = min(i, lon_ncart[j] - 2);
           double xa, ya, xb, yb;
-          grid_pos(pX, pY, uX, uY, Dr, seg, xa, ya);
-          grid_pos(pX, pY, uX, uY, Dr, seg + 1, xb, yb);
+          grid_pos(pP, pU, Dr, seg, xa, ya);
+          grid_pos(pP, pU, Dr, seg + 1, xb, yb);
           const double dxs = xb - xa, dys = yb - ya;
           const double h2 = dxs * dxs + dys * dys;
           double c, s;
@@ -455,77 +456,92 @@ __global__ void __launch_bounds__(kGridThreads, kGridMinCtas) fiss_grid_kernel(c
       }
     }
 
-    // ---- stage B, materialisation: lanes = flattened (candidate, time step) elements.
-    // When v_end is the fastest-numbered axis (FrenetOptimalPlanner order) the nv candidates of one lateral row
-    // have consecutive ids, i.e. their output rows are one contiguous run of nv*n_stride doubles (a "group");
-    // otherwise a group is a single candidate.  A group is cut into blocks of 31 output elements: the 32nd
-    // lane of a block only supplies the heading of the next step (kappa_m needs yaw_{m+1}), so blocks are
-    // independent and are dealt round-robin to the warps of the CTA.  Heading / ds / curvature as
-    // frenet_optimal_planner.py:121-134.
+    // ---- stage B, materialisation (calc_global_paths, frenet_optimal_planner.py:121-134).
+    // Lanes = flattened (longitudinal row j, time step m) elements f = j*n_stride + m of the frame tables, cut into
+    // blocks of 31 outputs: the 32nd lane of a block only supplies the heading of the next step (kappa_m needs
+    // yaw_{m+1}), so blocks are independent.  A task = (block, group of kMatRows lateral rows): the lane loads its two
+    // frame points (4 x LDS.128) and the speed once and walks the lateral rows of the group with them -- per
+    // lateral row two table reads, the position, the heading (polynomial atan2, csrc/fiss_math.cuh) and 1/ds; five
+    // coalesced stores.  The rows of a group are independent instruction chains (the loop is unrolled), which
+    // is what hides the FP64 latency at 2-3 resident CTAs per SM.
     if (kYaw) {
-      const int G = kContig ? nv : 1;          // candidates per group
-      const int n_groups = kContig ? rows_i : n_cand;
       const int ns = a.n_stride;
       const uint32_t ns_magic = (1u << 20) / (uint32_t)ns + 1u;  // f / ns for f < 2^20 / ns
-      const int f_end = G * ns;
-      const int blocks_per_group = (f_end + 30) / 31;
-      const uint32_t bpg_magic = (1u << 20) / (uint32_t)blocks_per_group + 1u;
-      // element offset of candidate (i0, j = 0, k) in a materialised row; groups follow at group_pitch
+      const int n_blocks = (nv * ns + 30) / 31;
+      const uint32_t nb_magic = (1u << 20) / (uint32_t)n_blocks + 1u;
+      const int n_groups = (rows_i + kMatRows - 1) / kMatRows;
+      // element offset of candidate (i0, j = 0, k) in a materialised row
       double* const mat_item = a.mat ? a.mat + ((int64_t)b * a.C + (int64_t)i0 * a.sd + (int64_t)k * a.st) * ns : nullptr;
-      const int64_t lat_pitch = (int64_t)a.sd * ns, lon_pitch = (int64_t)a.sv * ns;
-      for (int task = warp; task < n_groups * blocks_per_group; task += wpc) {
-        const int g = (int)(((uint32_t)task * bpg_magic) >> 20);
-        const int f = (task - g * blocks_per_group) * 31 + lane;
-        int ii, j, m;
-        if (kContig) {
-          ii = g;
-          j = min((int)(((uint32_t)f * ns_magic) >> 20), nv - 1);
-          m = f - j * ns;  // >= ns for the lanes past the end of the group
-        } else {
-          ii = (int)(((uint32_t)g * nv_magic) >> 20);
-          j = g - ii * nv;
-          m = f;
-        }
+      const int64_t lat_pitch = (int64_t)a.sd * ns;
+      const int lon_pitch = a.sv * ns;
+      for (int task = warp; task < n_groups * n_blocks; task += wpc) {
+        const int grp = (int)(((uint32_t)task * nb_magic) >> 20);
+        const int f = (task - grp * n_blocks) * 31 + lane;
+        const int j = min((int)(((uint32_t)f * ns_magic) >> 20), nv - 1);
+        const int m = f - j * ns;  // >= ns for the lanes past the end of the table
         const int tb = j * n_pad;
-        const double* Dr = lat + ii * n_pad;
         const int n_cart = lon_ncart[j];
-        const bool in_cart = m < n_cart;  // (n' <= n <= ns)
-        double xv = CUDART_NAN, yv = CUDART_NAN, yaw = CUDART_NAN, dx = 0.0, dy = 0.0, inv_ds = 0.0;
-        bool fast = false;
-        if (in_cart) {
-          if (n_cart >= 2) {
-            // yaw_m = atan2(dy, dx) of segment m for m < n'-1; the last point repeats the previous heading (:127-130)
-            const int seg = min(m, n_cart - 2);
-            double xa, ya, xb, yb;
-            grid_pos(PX + tb, PY + tb, UX + tb, UY + tb, Dr, seg, xa, ya);
-            grid_pos(PX + tb, PY + tb, UX + tb, UY + tb, Dr, seg + 1, xb, yb);
-            dx = xb - xa;
-            dy = yb - ya;
-            fast = segment_fast(dx, dy, yaw, inv_ds);
-            if (!fast) yaw = atan2(dy, dx);  // zero-length / non-finite segment: the library's special cases
-            xv = m == seg ? xa : xb;
-            yv = m == seg ? ya : yb;
-          } else {
-            grid_pos(PX + tb, PY + tb, UX + tb, UY + tb, Dr, m, xv, yv);  // n' == 1: yaw/ds/c stay empty (:121)
+        const bool in_cart = m < n_cart;                 // (n' <= n <= ns)
+        const bool has_seg = in_cart && n_cart >= 2;
+        // yaw_m = atan2 of segment min(m, n'-2): the last point repeats the previous heading (:127-130)
+        const int seg = has_seg ? min(m, n_cart - 2) : 0;
+        double2 Pa = make_double2(0.0, 0.0), Ua = Pa, Pb = Pa, Ub = Pa;
+        if (has_seg) {
+          Pa = P2[tb + seg];
+          Ua = U2[tb + seg];
+          Pb = P2[tb + seg + 1];
+          Ub = U2[tb + seg + 1];
+        } else if (in_cart) {  // n' == 1: the single point, yaw / ds / c stay empty (:121)
+          Pa = P2[tb + m];
+          Ua = U2[tb + m];
+        }
+        const bool at_seg = m == seg;
+        const bool has_kap = m < n_cart - 1;
+        const bool writes = mat_item != nullptr && lane < 31 && m < ns;
+        const double sd_v = m < n ? SD[tb + min(m, n_pad - 1)] : CUDART_NAN;
+        const int i_first = grp * kMatRows;
+        double* o = mat_item + ((int64_t)i_first * lat_pitch + (j * lon_pitch + m));
+#pragma unroll
+        for (int r = 0; r < kMatRows; ++r) {
+          const int ii = i_first + r;
+          if (ii < rows_i) {  // warp-uniform
+            const double* Dr = lat + ii * n_pad;
+            double xv = CUDART_NAN, yv = CUDART_NAN, yaw = CUDART_NAN, dx = 0.0, dy = 0.0, inv_ds = 0.0;
+            bool fast = false;
+            if (has_seg) {
+              const double da = Dr[seg], db = Dr[seg + 1];
+              const double xa = Pa.x - da * Ua.y, ya = Pa.y + da * Ua.x;
+              const double xb = Pb.x - db * Ub.y, yb = Pb.y + db * Ub.x;
+              dx = xb - xa;
+              dy = yb - ya;
+              fast = segment_fast(dx, dy, yaw, inv_ds);
+              if (!fast) yaw = atan2(dy, dx);  // zero-length / non-finite segment: the library's special cases
+              xv = at_seg ? xa : xb;
+              yv = at_seg ? ya : yb;
+            } else if (in_cart) {
+              const double da = Dr[m];
+              xv = Pa.x - da * Ua.y;
+              yv = Pa.y + da * Ua.x;
+            }
+            // the next step of the same row is the next lane; the last step of a row never looks at its
+            // neighbour (m >= n' - 1), and lane 31 writes nothing
+            const double yaw_next = __shfl_down_sync(kFull, yaw, 1);
+            double kap = CUDART_NAN;
+            if (has_kap) {
+              // c = dyaw / ds with ds = hypot(dx, dy) (:128,132; no unwrap; the last element is 0/ds)
+              kap = fast ? (yaw_next - yaw) * inv_ds : (yaw_next - yaw) / hypot(dx, dy);
+              if (p.check_curvature && lane < 31 && fabs(kap) > p.max_curvature)
+                atomicOr(&cflags[ii * nv + j], FISS_FLAG_CURVATURE);
+            }
+            if (writes) {
+              o[0] = xv;
+              o[row_pitch] = yv;
+              o[2 * row_pitch] = yaw;
+              o[3 * row_pitch] = sd_v;
+              o[4 * row_pitch] = kap;
+            }
+            o += lat_pitch;
           }
-        }
-        // the next step of the same candidate is the next lane; the last step of a candidate never looks at
-        // its neighbour (m >= n' - 1), and lane 31 writes nothing
-        const double yaw_next = __shfl_down_sync(kFull, yaw, 1);
-        double kap = CUDART_NAN;
-        if (m < n_cart - 1) {
-          // c = dyaw / ds with ds = hypot(dx, dy) (:128,132; no unwrap; the last element is 0/ds)
-          kap = fast ? (yaw_next - yaw) * inv_ds : (yaw_next - yaw) / hypot(dx, dy);
-          if (p.check_curvature && lane < 31 && fabs(kap) > p.max_curvature)
-            atomicOr(&cflags[ii * nv + j], FISS_FLAG_CURVATURE);
-        }
-        if (mat_item && lane < 31 && m < ns) {
-          double* o = mat_item + (ii * lat_pitch + j * lon_pitch + m);
-          o[0] = xv;
-          o[row_pitch] = yv;
-          o[2 * row_pitch] = yaw;
-          o[3 * row_pitch] = m < n ? SD[tb + m] : CUDART_NAN;
-          o[4 * row_pitch] = kap;
         }
       }
     }

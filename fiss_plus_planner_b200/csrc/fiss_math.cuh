@@ -37,36 +37,45 @@ __device__ __forceinline__ double atan_unit(double q) {
   return fma(q * u, fma(u, o, e), q);
 }
 
-// mn / mx for 0 <= mn <= mx, mx in the normal range: reciprocal seed + two Newton steps + one residual
-// correction (the generic division's special-case handling is not needed here); <= 1 ulp.
+// mn / mx for 0 <= mn <= mx, mx in the normal range: reciprocal seed (MUFU.RCP64H, ~2^-20), one cubic Newton
+// step r(1 + e + e^2) and one residual correction (the generic division's special cases are not needed); <= 1 ulp.
 __device__ __forceinline__ double ratio_unit(double mn, double mx) {
   double r;
   asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(mx));
-  double e = fma(-mx, r, 1.0);
-  r = fma(r, e, r);
-  e = fma(-mx, r, 1.0);
-  r = fma(r, e, r);
+  const double e = fma(-mx, r, 1.0);
+  r = fma(r, fma(e, e, e), r);
   const double q = mn * r;
   return fma(r, fma(-mx, q, mn), q);
 }
 
-// atan2 for a finite, non-degenerate vector (max(|x|, |y|) in the normal range); ~3e-16 relative.
-__device__ __forceinline__ double atan2_finite(double y, double x) {
-  const double ax = fabs(x), ay = fabs(y);
-  const bool steep = ay > ax;
-  const double mx = steep ? ay : ax, mn = steep ? ax : ay;
-  double a = atan_unit(ratio_unit(mn, mx));
-  if (steep) a = 1.5707963267948966 - a;
-  if (x < 0.0) a = 3.141592653589793 - a;
-  return copysign(a, y);
+// 1 / sqrt(h2) for h2 in the normal range: seed (MUFU.RSQ64H) + the cubic step y(1 + e/2 + 3e^2/8), e = 1 - h2 y^2
+// -- the same refinement the CUDA library's rsqrt() applies, without its special-case branch.
+__device__ __forceinline__ double rsqrt_normal(double h2) {
+  double y;
+  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(h2));
+  const double e = fma(-(h2 * y), y, 1.0);
+  return fma(y, fma(0.375, e, 0.5) * e, y);
 }
 
-// One segment (dx, dy): heading and 1/ds.  `ok` = the fast path applied (squared length in the normal range);
-// otherwise the caller uses the library (atan2 / hypot / division) to reproduce the reference's edge cases.
+// atan2 for a finite, non-degenerate vector (max(|x|, |y|) in the normal range); ~3e-16 relative.
+// Octant fix-up folded into one add: result = off + (+-a), off in {0, pi/2, pi}.
+__device__ __forceinline__ double atan2_finite(double y, double x) {
+  const double ax = fabs(x), ay = fabs(y);
+  const bool steep = ay > ax, neg = x < 0.0;
+  const double mx = steep ? ay : ax, mn = steep ? ax : ay;
+  const double a = atan_unit(ratio_unit(mn, mx));
+  const double off = steep ? 1.5707963267948966 : (neg ? 3.141592653589793 : 0.0);
+  const double sa = (steep != neg) ? -a : a;
+  return copysign(off + sa, y);
+}
+
+// One segment (dx, dy): heading and 1/ds.  `ok` = the fast path applied (squared length positive, finite and far
+// from both ends of the exponent range: 2^-767 <= h2 < 2^768, one integer test on the exponent field); otherwise the
+// caller uses the library (atan2 / hypot / division) to reproduce the reference's edge cases.
 __device__ __forceinline__ bool segment_fast(double dx, double dy, double& yaw, double& inv_ds) {
   const double h2 = fma(dx, dx, dy * dy);
-  if (!(h2 > 1.0e-280 && h2 < 1.0e280)) return false;
-  inv_ds = rsqrt(h2);
+  if (((unsigned)__double2hiint(h2) - 0x10000000u) >= 0x60000000u) return false;
+  inv_ds = rsqrt_normal(h2);
   yaw = atan2_finite(dy, dx);
   return true;
 }
