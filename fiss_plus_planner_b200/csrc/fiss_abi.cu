@@ -308,23 +308,13 @@ int32_t eval_grid(fiss_handle* h, cudaStream_t st, const double* d_ego, int B, c
   // obstacle rows of the checked steps go to shared memory while the CTA stays under the budget
   const int horizon = std::max(0, std::min(n_max, h->final_time_step - p->time_step_now));
   const int E_max = h->M > 0 ? (horizon + p->check_res - 1) / p->check_res : 0;
-  // preference order: rows + transposed centres in shared memory; transposed centres only (the rare exact
-  // tests read the rows from L2); neither (ballot path of stage A' on global rows)
+  // obstacle rows of the checked steps in shared memory while the CTA stays under the budget, else read from L2
   fiss::GridLayout L{};
-  const int tries[3][2] = {{E_max, E_max}, {0, E_max}, {0, 0}};
-  for (int t = 0; t < 3; ++t) {
-    a.E_stage = tries[t][0];
-    a.E_ot = tries[t][1];
-    L = fiss::grid_layout(a.Kp, a.Mp, a.E_stage, a.E_ot, a.nv, a.d_chunk, a.n_pad, a.e_pad, a.words);
-    if (L.bytes <= kSmemCtaBudget) break;
-  }
-  if (L.bytes > kSmemLimit) {  // over budget in every variant: take the first one that fits at all
-    for (int t = 0; t < 3; ++t) {
-      a.E_stage = tries[t][0];
-      a.E_ot = tries[t][1];
-      L = fiss::grid_layout(a.Kp, a.Mp, a.E_stage, a.E_ot, a.nv, a.d_chunk, a.n_pad, a.e_pad, a.words);
-      if (L.bytes <= kSmemLimit) break;
-    }
+  a.E_stage = E_max;
+  L = fiss::grid_layout(a.Kp, a.Mp, a.E_stage, a.nv, a.d_chunk, a.n_pad, a.e_pad, a.words);
+  if (L.bytes > kSmemCtaBudget) {
+    a.E_stage = 0;
+    L = fiss::grid_layout(a.Kp, a.Mp, a.E_stage, a.nv, a.d_chunk, a.n_pad, a.e_pad, a.words);
   }
   if (L.bytes > kSmemLimit) return fail(h, FISS_ERR_CAPACITY, "lattice row tables exceed 227 KB of shared memory");
   const bool yaw = d_mat != nullptr || p->check_curvature;

@@ -64,8 +64,7 @@ struct GridArgs {
   const double* obs_tab;    // [T_obs][4][Mp]
   const double* obs_const;  // [4][Mp]
   int32_t M, Mp, mp_shift, T_obs, final_time_step;
-  int32_t E_stage;     // obstacle rows staged in shared memory (0: read them from global/L2)
-  int32_t E_ot;        // checked steps in the transposed centre table (0: ballot path of stage A')
+  int32_t E_stage;     // obstacle rows staged in shared memory (0: read them from global / L2)
   int32_t words;       // 32-bit mask words per (row, step) = max(1, Mp/32)
   int32_t n_pad;       // table row length (>= max n + 1, even)
   int32_t e_pad;       // mask row length (>= max checked steps)
@@ -77,19 +76,20 @@ struct GridArgs {
 
 // Shared-memory carve-up (byte offsets, 16-byte aligned), used by the host for the launch size too.
 struct GridLayout {
-  uint32_t spline, oc, obs, ot, axes, lon, lat, lon_cost, lat_cost, dmax, lon_viol, lon_ncart, lon_E, npairs, pairs, cflags, masks, bytes;
+  uint32_t spline, oc, obs, bbox, axes, lon, lat, lon_cost, lat_cost, dmax, lon_viol, lon_ncart, lon_E, npairs, pairs, cflags, masks,
+      listed, near_list, bytes;
 };
 
 __host__ __device__ inline uint32_t grid_align16(uint32_t v) { return (v + 15u) & ~15u; }
 
-__host__ __device__ inline GridLayout grid_layout(int Kp, int Mp, int E_stage, int E_ot, int nv, int d_chunk,
-                                                  int n_pad, int e_pad, int words) {
+__host__ __device__ inline GridLayout grid_layout(int Kp, int Mp, int E_stage, int nv, int d_chunk, int n_pad, int e_pad,
+                                                  int words) {
   GridLayout L;
   uint32_t o = 16;  // two mbarriers
   L.spline = o;     o += 9u * Kp * 8u;
   L.oc = o;         o += 4u * Mp * 8u;
   L.obs = o;        o += (uint32_t)E_stage * 4u * Mp * 8u;
-  L.ot = o;         o += (uint32_t)E_ot * 2u * Mp * 8u;
+  L.bbox = o;       o += (uint32_t)e_pad * 4u * 8u;
   L.axes = o;       o += 4u * kAxisMax * 8u;
   L.lon = o;        o += 5u * nv * n_pad * 8u;
   L.lat = o;        o += (uint32_t)d_chunk * n_pad * 8u;
@@ -103,9 +103,15 @@ __host__ __device__ inline GridLayout grid_layout(int Kp, int Mp, int E_stage, i
   L.pairs = o;      o += grid_align16((uint32_t)nv * e_pad * 4u);
   L.cflags = o;     o += grid_align16((uint32_t)d_chunk * nv * 4u);
   L.masks = o;      o += grid_align16((uint32_t)nv * e_pad * words * 4u);
+  L.listed = o;     o += grid_align16((uint32_t)nv * e_pad * 4u);
+  L.near_list = o;  o += grid_align16((uint32_t)e_pad * Mp * 4u);
   L.bytes = o;
   return L;
 }
+
+// Squared distance, one expression for the box test and the per-row test of stage A' (so that rounding is monotone:
+// |bx| <= |dx| and |by| <= |dy| imply near2(bx, by) <= near2(dx, dy) bit for bit).
+__device__ __forceinline__ double near2(double dx, double dy) { return fma(dx, dx, dy * dy); }
 
 // Candidate position at step m from the row tables (same expression as the generic kernel:
 // x = px - d*(ty*r), y = py + d*(tx*r) with the unit tangent stored already multiplied out).
@@ -122,12 +128,12 @@ __device__ __forceinline__ void grid_pos(const double2* __restrict__ P2, const d
 template <bool kYaw>
 __global__ void __launch_bounds__(kGridThreads, kGridMinCtas) fiss_grid_kernel(const GridArgs a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  const GridLayout L = grid_layout(a.Kp, a.Mp, a.E_stage, a.E_ot, a.nv, a.d_chunk, a.n_pad, a.e_pad, a.words);
+  const GridLayout L = grid_layout(a.Kp, a.Mp, a.E_stage, a.nv, a.d_chunk, a.n_pad, a.e_pad, a.words);
   uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw);  // [0] spline, [1] obstacles
   double* sp = reinterpret_cast<double*>(smem_raw + L.spline);
   double* oc = reinterpret_cast<double*>(smem_raw + L.oc);
   double* obs_s = reinterpret_cast<double*>(smem_raw + L.obs);
-  double* ot = reinterpret_cast<double*>(smem_raw + L.ot);  // [2][Mp][E_ot]: obstacle centres, step-minor
+  double* bbox = reinterpret_cast<double*>(smem_raw + L.bbox);  // [e_pad][4]: x_min, x_max, y_min, y_max of the frame points
   double* ax = reinterpret_cast<double*>(smem_raw + L.axes);
   double* lon = reinterpret_cast<double*>(smem_raw + L.lon);
   double* lat = reinterpret_cast<double*>(smem_raw + L.lat);
@@ -141,6 +147,9 @@ __global__ void __launch_bounds__(kGridThreads, kGridMinCtas) fiss_grid_kernel(c
   uint32_t* pairs = reinterpret_cast<uint32_t*>(smem_raw + L.pairs);      // (row << 16 | checked step) with any proximity bit
   uint32_t* cflags = reinterpret_cast<uint32_t*>(smem_raw + L.cflags);    // per candidate: collision / curvature bits
   uint32_t* masks = reinterpret_cast<uint32_t*>(smem_raw + L.masks);
+  uint32_t* listed = reinterpret_cast<uint32_t*>(smem_raw + L.listed);        // (row, step) already on the work list
+  uint32_t* near_list = reinterpret_cast<uint32_t*>(smem_raw + L.near_list);  // (step << 16 | obstacle) that passed the box
+  uint32_t* n_near = npairs + 1;
 
   const fiss_params& p = a.p;
   const int warp = threadIdx.x >> 5;
@@ -185,15 +194,6 @@ __global__ void __launch_bounds__(kGridThreads, kGridMinCtas) fiss_grid_kernel(c
   const double* obs = a.E_stage > 0 ? obs_s : a.obs_tab;
   const int obs_row0 = a.E_stage > 0 ? 0 : p.time_step_now;
   const int obs_row_step = a.E_stage > 0 ? 1 : p.check_res;
-  // transposed centres OT[c][jo][e] (lanes that are consecutive checked steps read consecutive doubles)
-  for (int q = threadIdx.x; q < a.E_ot * Mp; q += blockDim.x) {
-    const int e = q / Mp, jo = q - e * Mp;
-    const int row = obs_row0 + e * obs_row_step;
-    const bool in_tab = a.E_stage > 0 ? e < a.E_stage : row < a.T_obs;
-    const double* slot = obs + row * (4 * Mp) + jo;
-    ot[jo * a.E_ot + e] = in_tab ? slot[0] : kObsFar;
-    ot[(Mp + jo) * a.E_ot + e] = in_tab ? slot[Mp] : kObsFar;
-  }
   const double hle = 0.5 * p.ego_length, hwe = 0.5 * p.ego_width;
   const double re = sqrt(hle * hle + hwe * hwe);
 
@@ -220,6 +220,7 @@ __global__ void __launch_bounds__(kGridThreads, kGridMinCtas) fiss_grid_kernel(c
     if (threadIdx.x == 0) {
       *dmax_bits = 0ull;
       *npairs = 0u;
+      *n_near = 0u;
     }
     for (int q = threadIdx.x; q < n_cand; q += blockDim.x) cflags[q] = 0u;
     const double T = ax[2 * kAxisMax + k];
@@ -314,90 +315,67 @@ __global__ void __launch_bounds__(kGridThreads, kGridMinCtas) fiss_grid_kernel(c
     }
     __syncthreads();
 
-    // ---- stage A': proximity masks.  Lanes = obstacles; a warp takes checked steps, keeps the obstacle
-    // centres of that step in registers and walks the longitudinal rows: one ballot per (row, step).
+    // ---- stage A': proximity masks.  masks[j][e] gets a bit per obstacle whose centre is within
+    // (max|d| + r_ego + r_obs) of the frame point of longitudinal row j at checked step e -- a superset of the
+    // obstacles any candidate on that row can touch there.  Three short passes:
+    //   (1) one lane per checked step boxes the frame points of the rows that check that step;
+    //   (2) one lane per (step, obstacle) tests the obstacle against the box (the same squared-distance expression
+    //       as the per-row test, so the box can only over-accept); the few survivors go to a compact list;
+    //   (3) one lane per (survivor, row) runs the per-row test, sets the mask bit and -- the first one to touch a
+    //       (row, step) -- appends it to the work list of stage B.
     if (a.M > 0) {
       const double dmax = __longlong_as_double((long long)*dmax_bits);
       const double reach0 = (dmax + re) * (1.0 + 1.0e-9) + 1.0e-9;
-      if (a.E_ot > 0) {
-        // one LANE per (row, checked step): walk the obstacles, build the mask words in registers
-        const uint32_t ep_magic = (1u << 20) / (uint32_t)e_pad + 1u;
-        for (int q = threadIdx.x; q < nv * e_pad; q += blockDim.x) {
-          const int j = (int)(((uint32_t)q * ep_magic) >> 20);
-          const int e = q - j * e_pad;
-          const bool live = e < lon_E[j] && e < a.E_ot;
-          uint32_t any = 0u;
-          if (live) {
-            const double2 fp = P2[j * n_pad + e * res];
-            const double fx = fp.x, fy = fp.y;
-            const double* ox = ot + e;
-            const double* oy = ot + Mp * a.E_ot + e;
-            for (int w = 0; w < words; ++w) {
-              uint32_t bits = 0u;
-              const int jo_end = min(a.M, w * 32 + 32);
-              for (int jo = w * 32; jo < jo_end; ++jo) {
-                const double dx = ox[jo * a.E_ot] - fx, dy = oy[jo * a.E_ot] - fy;
-                const double reach = reach0 + oc[2 * Mp + jo] * (1.0 + 1.0e-9);
-                if (dx * dx + dy * dy <= reach * reach) bits |= 1u << (jo & 31);
-              }
-              masks[q * words + w] = bits;
-              any |= bits;
-            }
-          } else {
-            for (int w = 0; w < words; ++w) masks[q * words + w] = 0u;
-          }
-          if (any) pairs[atomicAdd(npairs, 1u)] = ((uint32_t)j << 16) | (uint32_t)e;
-        }
-      } else if (Mp <= 32) {
-        const int jo = lane & (Mp - 1);
-        const int sub = lane >> a.mp_shift;
-        const int ppi = 32 >> a.mp_shift;  // checked steps per warp iteration
-        const double reach = reach0 + oc[2 * Mp + jo] * (1.0 + 1.0e-9);
-        const double reach2 = reach * reach;
-        const uint32_t sub_mask = Mp == 32 ? 0xffffffffu : ((1u << Mp) - 1u);
-        const int sub_shift = sub * Mp;
-        for (int e0 = warp * ppi; e0 < e_pad; e0 += wpc * ppi) {
-          const int e = e0 + sub;
-          const int row = obs_row0 + e * obs_row_step;
-          const bool in_tab = a.E_stage > 0 ? e < a.E_stage : (e < e_pad && row < a.T_obs);
-          const double* slot = obs + row * (4 * Mp) + jo;
-          const double ox = in_tab ? slot[0] : kObsFar, oy = in_tab ? slot[Mp] : kObsFar;
-          const int m = min(e * res, n_pad - 1);
-          for (int j = 0; j < nv; ++j) {
+      for (int e = threadIdx.x; e < e_pad; e += blockDim.x) {
+        double x0 = CUDART_INF, x1 = -CUDART_INF, y0 = CUDART_INF, y1 = -CUDART_INF;
+        const int m = min(e * res, n_pad - 1);
+        for (int j = 0; j < nv; ++j) {
+          if (e < lon_E[j]) {
             const double2 fp = P2[j * n_pad + m];
-            const double dx = ox - fp.x, dy = oy - fp.y;
-            const bool near = e < lon_E[j] && dx * dx + dy * dy <= reach2;
-            const uint32_t word = (__ballot_sync(kFull, near) >> sub_shift) & sub_mask;
-            if (jo == 0 && e < e_pad) {
-              masks[j * e_pad + e] = word;
-              if (word) pairs[atomicAdd(npairs, 1u)] = ((uint32_t)j << 16) | (uint32_t)e;
-            }
+            x0 = fmin(x0, fp.x);
+            x1 = fmax(x1, fp.x);
+            y0 = fmin(y0, fp.y);
+            y1 = fmax(y1, fp.y);
           }
+          listed[j * e_pad + e] = 0u;
+          for (int w = 0; w < words; ++w) masks[(j * e_pad + e) * words + w] = 0u;
         }
-      } else {
-        for (int e = warp; e < e_pad; e += wpc) {
-          const int row = obs_row0 + e * obs_row_step;
-          const bool in_tab = a.E_stage > 0 ? e < a.E_stage : row < a.T_obs;
-          const int m = e * res;
-          for (int j = 0; j < nv; ++j) {
-            const bool live = in_tab && e < lon_E[j];
-            const double2 fp = live ? P2[j * n_pad + m] : make_double2(0.0, 0.0);
-            const double fx = fp.x, fy = fp.y;
-            uint32_t any = 0u;
-            for (int w = 0; w < words; ++w) {
-              const int jo = w * 32 + lane;
-              bool near = false;
-              if (live) {
-                const double* slot = obs + row * (4 * Mp) + jo;
-                const double reach = reach0 + oc[2 * Mp + jo] * (1.0 + 1.0e-9);
-                const double dx = slot[0] - fx, dy = slot[Mp] - fy;
-                near = dx * dx + dy * dy <= reach * reach;
-              }
-              const uint32_t ball = __ballot_sync(kFull, near);
-              if (lane == 0) masks[(j * e_pad + e) * words + w] = ball;
-              any |= ball;
-            }
-            if (lane == 0 && any) pairs[atomicAdd(npairs, 1u)] = ((uint32_t)j << 16) | (uint32_t)e;
+        bbox[4 * e + 0] = x0;  // no row checks this step: the empty box (+inf, -inf) is infinitely far from everything
+        bbox[4 * e + 1] = x1;
+        bbox[4 * e + 2] = y0;
+        bbox[4 * e + 3] = y1;
+      }
+      __syncthreads();
+      const uint32_t mp_magic = (1u << 20) / (uint32_t)Mp + 1u;  // q / Mp for q < 2^20 / Mp
+      for (int q = threadIdx.x; q < e_pad * Mp; q += blockDim.x) {
+        const int e = (int)(((uint32_t)q * mp_magic) >> 20);
+        const int jo = q - e * Mp;
+        const int row = obs_row0 + e * obs_row_step;
+        const bool in_tab = a.E_stage > 0 ? e < a.E_stage : row < a.T_obs;
+        if (jo < a.M && in_tab) {
+          const double* slot = obs + row * (4 * Mp) + jo;
+          const double ox = slot[0], oy = slot[Mp];
+          const double reach = reach0 + oc[2 * Mp + jo] * (1.0 + 1.0e-9);
+          const double bx = fmax(fmax(bbox[4 * e] - ox, ox - bbox[4 * e + 1]), 0.0);
+          const double by = fmax(fmax(bbox[4 * e + 2] - oy, oy - bbox[4 * e + 3]), 0.0);
+          if (near2(bx, by) <= reach * reach) near_list[atomicAdd(n_near, 1u)] = ((uint32_t)e << 16) | (uint32_t)jo;
+        }
+      }
+      __syncthreads();
+      const uint32_t n_cand_pairs = *n_near * (uint32_t)nv;
+      for (uint32_t q = threadIdx.x; q < n_cand_pairs; q += blockDim.x) {
+        const uint32_t c = q / (uint32_t)nv;
+        const int j = (int)(q - c * (uint32_t)nv);
+        const uint32_t ej = near_list[c];
+        const int e = (int)(ej >> 16), jo = (int)(ej & 0xffffu);
+        if (e < lon_E[j]) {
+          const double* slot = obs + (obs_row0 + e * obs_row_step) * (4 * Mp) + jo;
+          const double2 fp = P2[j * n_pad + e * res];
+          const double reach = reach0 + oc[2 * Mp + jo] * (1.0 + 1.0e-9);
+          if (near2(slot[0] - fp.x, slot[Mp] - fp.y) <= reach * reach) {
+            atomicOr(&masks[(j * e_pad + e) * words + (jo >> 5)], 1u << (jo & 31));
+            if (atomicExch(&listed[j * e_pad + e], 1u) == 0u)
+              pairs[atomicAdd(npairs, 1u)] = ((uint32_t)j << 16) | (uint32_t)e;
           }
         }
       }
@@ -483,64 +461,57 @@ __global__ void __launch_bounds__(kGridThreads, kGridMinCtas) fiss_grid_kernel(c
         const int n_cart = lon_ncart[j];
         const bool in_cart = m < n_cart;                 // (n' <= n <= ns)
         const bool has_seg = in_cart && n_cart >= 2;
+        const bool lone = in_cart && n_cart < 2;         // n' == 1: the single point; yaw / ds / c stay empty (:121)
         // yaw_m = atan2 of segment min(m, n'-2): the last point repeats the previous heading (:127-130)
         const int seg = has_seg ? min(m, n_cart - 2) : 0;
-        double2 Pa = make_double2(0.0, 0.0), Ua = Pa, Pb = Pa, Ub = Pa;
-        if (has_seg) {
-          Pa = P2[tb + seg];
-          Ua = U2[tb + seg];
-          Pb = P2[tb + seg + 1];
-          Ub = U2[tb + seg + 1];
-        } else if (in_cart) {  // n' == 1: the single point, yaw / ds / c stay empty (:121)
-          Pa = P2[tb + m];
-          Ua = U2[tb + m];
-        }
+        // Lanes outside the Cartesian part carry NaN frame points: x, y, heading and curvature come out NaN by
+        // propagation, so the per-row code below is straight-line for every lane.
+        const double2 nan2 = make_double2(CUDART_NAN, CUDART_NAN);
+        const double2 Pa = in_cart ? P2[tb + seg] : nan2;
+        const double2 Ua = U2[tb + seg];
+        const double2 Pb = in_cart ? P2[tb + seg + 1] : nan2;
+        const double2 Ub = U2[tb + seg + 1];
         const bool at_seg = m == seg;
         const bool has_kap = m < n_cart - 1;
         const bool writes = mat_item != nullptr && lane < 31 && m < ns;
         const double sd_v = m < n ? SD[tb + min(m, n_pad - 1)] : CUDART_NAN;
         const int i_first = grp * kMatRows;
+        const double* Dr = lat + i_first * n_pad + seg;
         double* o = mat_item + ((int64_t)i_first * lat_pitch + (j * lon_pitch + m));
 #pragma unroll
         for (int r = 0; r < kMatRows; ++r) {
-          const int ii = i_first + r;
-          if (ii < rows_i) {  // warp-uniform
-            const double* Dr = lat + ii * n_pad;
-            double xv = CUDART_NAN, yv = CUDART_NAN, yaw = CUDART_NAN, dx = 0.0, dy = 0.0, inv_ds = 0.0;
-            bool fast = false;
-            if (has_seg) {
-              const double da = Dr[seg], db = Dr[seg + 1];
-              const double xa = Pa.x - da * Ua.y, ya = Pa.y + da * Ua.x;
-              const double xb = Pb.x - db * Ub.y, yb = Pb.y + db * Ub.x;
-              dx = xb - xa;
-              dy = yb - ya;
-              fast = segment_fast(dx, dy, yaw, inv_ds);
-              if (!fast) yaw = atan2(dy, dx);  // zero-length / non-finite segment: the library's special cases
-              xv = at_seg ? xa : xb;
-              yv = at_seg ? ya : yb;
-            } else if (in_cart) {
-              const double da = Dr[m];
-              xv = Pa.x - da * Ua.y;
-              yv = Pa.y + da * Ua.x;
+          if (i_first + r < rows_i) {  // warp-uniform
+            const double da = Dr[0], db = Dr[1];
+            const double xa = Pa.x - da * Ua.y, ya = Pa.y + da * Ua.x;
+            const double xb = Pb.x - db * Ub.y, yb = Pb.y + db * Ub.x;
+            const double dx = xb - xa, dy = yb - ya;
+            double yaw, inv_ds;
+            // a zero-length / non-finite segment takes the library (its special cases are the reference's)
+            const bool odd = !segment_fast(dx, dy, yaw, inv_ds) && has_seg;
+            if (__any_sync(kFull, odd || lone)) {  // rare, warp-uniform
+              if (odd) yaw = atan2_library(dy, dx);
+              if (lone) yaw = CUDART_NAN;
             }
             // the next step of the same row is the next lane; the last step of a row never looks at its
             // neighbour (m >= n' - 1), and lane 31 writes nothing
             const double yaw_next = __shfl_down_sync(kFull, yaw, 1);
-            double kap = CUDART_NAN;
-            if (has_kap) {
-              // c = dyaw / ds with ds = hypot(dx, dy) (:128,132; no unwrap; the last element is 0/ds)
-              kap = fast ? (yaw_next - yaw) * inv_ds : (yaw_next - yaw) / hypot(dx, dy);
-              if (p.check_curvature && lane < 31 && fabs(kap) > p.max_curvature)
-                atomicOr(&cflags[ii * nv + j], FISS_FLAG_CURVATURE);
+            // c = dyaw / ds with ds = hypot(dx, dy) (:128,132; no unwrap; the last element is 0/ds)
+            double kap = (yaw_next - yaw) * inv_ds;
+            if (__any_sync(kFull, odd)) {
+              if (odd) kap = div_hypot_library(yaw_next - yaw, dx, dy);
             }
+            kap = has_kap ? kap : CUDART_NAN;
+            if (p.check_curvature && has_kap && lane < 31 && fabs(kap) > p.max_curvature)
+              atomicOr(&cflags[(i_first + r) * nv + j], FISS_FLAG_CURVATURE);
             if (writes) {
-              o[0] = xv;
-              o[row_pitch] = yv;
+              o[0] = at_seg ? xa : xb;
+              o[row_pitch] = at_seg ? ya : yb;
               o[2 * row_pitch] = yaw;
               o[3 * row_pitch] = sd_v;
               o[4 * row_pitch] = kap;
             }
             o += lat_pitch;
+            Dr += n_pad;
           }
         }
       }

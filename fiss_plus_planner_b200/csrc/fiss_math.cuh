@@ -69,15 +69,19 @@ __device__ __forceinline__ double atan2_finite(double y, double x) {
   return copysign(off + sa, y);
 }
 
-// One segment (dx, dy): heading and 1/ds.  `ok` = the fast path applied (squared length positive, finite and far
-// from both ends of the exponent range: 2^-767 <= h2 < 2^768, one integer test on the exponent field); otherwise the
-// caller uses the library (atan2 / hypot / division) to reproduce the reference's edge cases.
+// One segment (dx, dy): heading and 1/ds, straight-line for every input.  Returns true when the result is valid:
+// squared length positive, finite and far from both ends of the exponent range (2^-767 <= h2 < 2^768, one integer
+// test on the exponent field).  Otherwise (zero-length / non-finite segment) the outputs are unspecified and the
+// caller takes the library (atan2 / hypot / division), whose special cases are the reference's.
 __device__ __forceinline__ bool segment_fast(double dx, double dy, double& yaw, double& inv_ds) {
   const double h2 = fma(dx, dx, dy * dy);
-  if (((unsigned)__double2hiint(h2) - 0x10000000u) >= 0x60000000u) return false;
   inv_ds = rsqrt_normal(h2);
   yaw = atan2_finite(dy, dx);
-  return true;
+  return ((unsigned)__double2hiint(h2) - 0x10000000u) < 0x60000000u;
 }
+
+// Out-of-line library calls for the rare lanes (kept out of the hot loop's register budget).
+__device__ __noinline__ double atan2_library(double y, double x) { return atan2(y, x); }
+__device__ __noinline__ double div_hypot_library(double num, double dx, double dy) { return num / hypot(dx, dy); }
 
 }  // namespace fiss
