@@ -171,7 +171,13 @@ def run_ours(args):
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    saved_stdout = None
     if world > 1:
+        # NCCL prints its version banner on stdout when the communicator is created; stdout must carry exactly ONE
+        # JSON line, so everything else goes to stderr until the line is printed
+        sys.stdout.flush()
+        saved_stdout = os.dup(1)
+        os.dup2(2, 1)
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     n_gpus = world
@@ -351,7 +357,11 @@ def run_ours(args):
         if cpu is not None:
             line["cpu_baseline"] = {"value": cpu["value"], "unit": UNIT, "cores": cpu["cores"], "kind": "port",
                                     "sample": cpu["sample"]}
-        print(json.dumps(line))
+        if saved_stdout is not None:
+            sys.stdout.flush()
+            os.write(saved_stdout, (json.dumps(line) + "\n").encode())
+        else:
+            print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
 

@@ -36,7 +36,10 @@
 
 namespace fiss {
 
-constexpr int kGridWarps = 8;
+#ifndef FISS_GRID_WARPS
+#define FISS_GRID_WARPS 8
+#endif
+constexpr int kGridWarps = FISS_GRID_WARPS;
 constexpr int kGridThreads = kGridWarps * 32;
 #ifndef FISS_GRID_MIN_CTAS
 #define FISS_GRID_MIN_CTAS 3
