@@ -154,6 +154,86 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
+# ------------------------------------------------------------------------------------------------ closed loop
+CLOSED_LOOP_SCENARIO = "DEU_Flensburg-1_1_T-1"   # BASELINE configs[0] (scripts/demo_cr.py, lattice 5x5x5)
+
+
+def _load_fixture_scenario(tmpdir):
+    import gzip
+    from fiss_plus_planner_b200.planners.commonroad_interface.commonroad_lite import CommonRoadFileReader
+    src = os.path.join(ROOT, "tests", "golden", "scenario_%s.xml.gz" % CLOSED_LOOP_SCENARIO)
+    if not os.path.exists(src):
+        return None
+    dst = os.path.join(tmpdir, CLOSED_LOOP_SCENARIO + ".xml")
+    with gzip.open(src, "rb") as g, open(dst, "wb") as f:
+        f.write(g.read())
+    scenario, pps = CommonRoadFileReader(dst).open()
+    return scenario, list(pps.planning_problem_dict.values())[0]
+
+
+def closed_loop_ours(device: int):
+    """plan()-cycle latency of the four drop-in planners inside frenet_optimal_planning() on the config-1 scenario
+    (reader -> route -> frame -> one CUDA plan() per 0.1 s step, ego advanced from the winner)."""
+    import tempfile
+    from fiss_plus_planner_b200.planners.benchmark.planning import frenet_optimal_planning
+    from fiss_plus_planner_b200.planners.commonroad_interface.vehicle_parameters import VehicleParameterMapping
+    out = {"scenario": CLOSED_LOOP_SCENARIO, "lattice": [5, 5, 5], "note": "wall time of planner.plan() per cycle, "
+           "as planning.py:124-128 measures it (host marshalling + H2D + kernels + D2H + host search)"}
+    with tempfile.TemporaryDirectory() as tmp:
+        loaded = _load_fixture_scenario(tmp)
+        if loaded is None:
+            return None
+        scenario, problem = loaded
+        vp = VehicleParameterMapping["VW_VANAGON"].value
+        for method in ("FOP", "FOP+", "FISS", "FISS+"):
+            frenet_optimal_planning(scenario, problem, vp, method, (5, 5, 5), verbose=False, device=device)  # warm-up run
+            reached, traj, avg_t, times, stats, _ = frenet_optimal_planning(scenario, problem, vp, method, (5, 5, 5),
+                                                                            verbose=False, device=device)
+            out[method] = {"p50_ms": 1e3 * float(np.median(times)), "mean_ms": 1e3 * float(np.mean(times)),
+                           "cycles": len(times), "goal_reached": bool(reached),
+                           "generated_per_cycle": float(stats.num_trajs_generated)}
+    return out
+
+
+def closed_loop_cpu_port(cycles: int = 3):
+    """The same scenario through the oracle port of FrenetOptimalPlanner.plan() (1 core, like the reference)."""
+    import tempfile
+    from fiss_plus_planner_b200.planners.commonroad_interface.global_planner import GlobalPlanner
+    from fiss_plus_planner_b200.planners.commonroad_interface.vehicle_parameters import VehicleParameterMapping
+    from fiss_plus_planner_b200.planners.common.scenario.frenet import FrenetState, State
+    from fiss_plus_planner_b200.planners.common.vehicle.vehicle import Vehicle
+    from fiss_plus_planner_b200.planners.frenet_optimal_planner import marshal_obstacles
+    from oracle import fop_oracle as fo
+    with tempfile.TemporaryDirectory() as tmp:
+        loaded = _load_fixture_scenario(tmp)
+        if loaded is None:
+            return None
+        scenario, problem = loaded
+    veh = Vehicle(VehicleParameterMapping["VW_VANAGON"].value)
+    pts = GlobalPlanner().plan_global_route(scenario, problem).concat_centerline
+    opl = fo.FopOracle(fo.Settings(5, 5, 5), veh.l, veh.w, veh.max_speed, veh.max_accel)
+    opl.generate_frenet_frame(pts)
+    tab = marshal_obstacles(scenario.static_obstacles + scenario.dynamic_obstacles)
+    obs = fo.ObstacleTable(tab.xyth, tab.lw, tab.valid.astype(bool), tab.final_time_step)
+    # start state as the driver computes it
+    from fiss_plus_planner_b200.planners.common.geometry.cubic_spline import CubicSpline2D
+    csp = CubicSpline2D(pts[:, 0], pts[:, 1])
+    ss = np.arange(0, csp.s[-1], 0.1)
+    ref = np.column_stack(([csp.calc_position(v) for v in ss], [csp.calc_yaw(v) for v in ss], [csp.calc_curvature(v) for v in ss]))
+    init = problem.initial_state
+    fs = FrenetState()
+    fs.from_state(State(t=0.0, x=init.position[0], y=init.position[1], yaw=init.orientation, v=init.velocity, a=init.acceleration), ref)
+    ego6 = (fs.s, fs.s_d, fs.s_dd, fs.d, fs.d_d, fs.d_dd)
+    times = []
+    for i in range(cycles):
+        t0 = time.perf_counter()
+        tr = opl.plan(ego6, 13.5, obs, i)
+        times.append(time.perf_counter() - t0)
+        ego6 = (tr.s[1], tr.s_d[1], tr.s_dd[1], tr.d[1], tr.d_d[1], tr.d_dd[1])
+    return {"FOP": {"p50_ms": 1e3 * float(np.median(times)), "cycles": cycles, "cores": 1,
+                    "kind": "port (oracle FopOracle.plan, NumPy SAT in place of shapely/GEOS)"}}
+
+
 # ------------------------------------------------------------------------------------------------ ours
 def algorithmic_bytes(end, batch, num_obs, num_knots):
     """SURVEY 8(d), full-materialisation FP64: per candidate 5*n*8 + 16; per problem the tables read once."""
@@ -317,6 +397,11 @@ def run_ours(args):
             lat.append(time.perf_counter() - t1)
         p50 = 1e3 * float(np.median(lat))
         eng2.close()
+    closed = None
+    if rank == 0 and n_gpus == 1 and not args.no_closed_loop:
+        closed = closed_loop_ours(local_rank)
+        if closed is not None and not args.no_cpu_baseline:
+            closed["cpu"] = closed_loop_cpu_port()
 
     if rank == 0:
         peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
@@ -354,6 +439,8 @@ def run_ours(args):
             "plan_cycle_config": "config 2: 1 ego state, 270 candidates, 8 obstacles, fiss_plan_grid_host incl. H2D/D2H",
             "clocks": clocks,
         }
+        if closed is not None:
+            line["closed_loop"] = closed
         if cpu is not None:
             line["cpu_baseline"] = {"value": cpu["value"], "unit": UNIT, "cores": cpu["cores"], "kind": "port",
                                     "sample": cpu["sample"]}
@@ -400,6 +487,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch-per-gpu", type=int, default=BATCH_PER_GPU)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-closed-loop", action="store_true", help="skip the config-1 closed-loop latency section")
     ap.add_argument("--cpu-steps", type=int, default=150,
                     help="CPU-baseline sample: lattices evaluated by the oracle port (150 x ~80 ms = ~12 s of host time)")
     args = ap.parse_args()

@@ -78,7 +78,7 @@ struct fiss_handle {
   DevBuf obs_tab, obs_const, obs_raw, obs_lw, obs_valid;
   int M = 0, Mp = 0, mp_shift = 0, T_obs = 0, final_time_step = 0;
   // *_host staging
-  DevBuf d_ego, d_end, d_cost, d_flags, d_best_idx, d_best_cost, d_meta, d_records, d_sel;
+  DevBuf d_ego, d_end, d_cost, d_flags, d_best_idx, d_best_cost, d_meta, d_records, d_es;  // d_es: in/out block of fiss_eval_end_states_host
   PinBuf h_in, h_out;
   std::vector<double> end_cache;
   // product lattice (fiss_grid): device axes [4][kAxisMax] + the expanded [C][4] table in d_end
@@ -365,7 +365,7 @@ int32_t fiss_destroy(fiss_handle* h) {
   cudaSetDevice(h->device);
   for (DevBuf* b : {&h->spline, &h->obs_tab, &h->obs_const, &h->obs_raw, &h->obs_lw, &h->obs_valid, &h->d_ego,
                     &h->d_end, &h->d_cost, &h->d_flags, &h->d_best_idx, &h->d_best_cost, &h->d_meta, &h->d_records,
-                    &h->d_sel, &h->d_axes})
+                    &h->d_es, &h->d_axes})
     b->release();
   h->h_in.release();
   h->h_out.release();
@@ -538,14 +538,9 @@ int32_t fiss_pick_winners_dev(fiss_handle* h, void* stream, const double* d_ego,
   if (rc != FISS_OK) return rc;
   FISS_CUDA(h, cudaSetDevice(h->device));
   cudaStream_t st = (cudaStream_t)stream;
-  fiss::fiss_pick_kernel<<<B, fiss::kPickThreads, 0, st>>>(d_cost, d_flags, C, d_best_idx, d_best_cost);
+  fiss::fiss_pick_kernel<<<B, fiss::kPickThreads, 0, st>>>(d_cost, d_flags, C, d_best_idx, d_best_cost, d_end, d_best_meta);
   h->launches++;
   FISS_CUDA(h, cudaGetLastError());
-  if (d_best_meta) {
-    fiss::fiss_meta_kernel<<<(B + 127) / 128, 128, 0, st>>>(d_best_idx, d_end, d_flags, B, C, d_best_meta);
-    h->launches++;
-    FISS_CUDA(h, cudaGetLastError());
-  }
   if (d_records) {
     LaunchPlan lp{};
     rc = plan_launch(h, p, B, n_stride, lp);
@@ -591,18 +586,20 @@ static int32_t plan_common(fiss_handle* h, cudaStream_t st, const double* ego, i
   FISS_CUDA(h, h->d_ego.ensure((size_t)B * 48));
   FISS_CUDA(h, h->d_cost.ensure(total * 8));
   FISS_CUDA(h, h->d_flags.ensure(total * 4));
-  FISS_CUDA(h, h->d_best_idx.ensure((size_t)B * 4));
-  FISS_CUDA(h, h->d_best_cost.ensure((size_t)B * 8));
-  FISS_CUDA(h, h->d_meta.ensure((size_t)B * 8));
+  // winners: one device block [best_cost B x 8 | meta B x 8 | best_idx B x 4] so that they travel in ONE copy
+  const size_t w_cost = 0, w_meta = (size_t)B * 8, w_idx = (size_t)B * 16, w_bytes = (size_t)B * 20;
+  FISS_CUDA(h, h->d_best_cost.ensure(w_bytes));
+  char* dw = h->d_best_cost.as<char>();
+  double* d_bcost = reinterpret_cast<double*>(dw + w_cost);
+  int32_t* d_bmeta = reinterpret_cast<int32_t*>(dw + w_meta);
+  int32_t* d_bidx = reinterpret_cast<int32_t*>(dw + w_idx);
   if (records) FISS_CUDA(h, h->d_records.ensure(rec_doubles * 8));
-  // pinned staging: [ego] in, [best_cost | records | cost | best_idx | meta | flags] out -- each piece only when
-  // the caller's own buffer is not page-locked (a pinned caller buffer is the DMA source / target itself)
-  const bool pin_ego = host_is_pinned(ego), pin_cost = host_is_pinned(best_cost), pin_idx = host_is_pinned(best_idx),
-             pin_meta = host_is_pinned(best_meta), pin_rec = host_is_pinned(records), pin_vol = host_is_pinned(cost),
+  // pinned staging: [ego] in, [winners | records | cost | flags] out -- the big pieces only when the caller's own
+  // buffer is not page-locked (a pinned caller buffer is the DMA source / target itself)
+  const bool pin_ego = host_is_pinned(ego), pin_rec = host_is_pinned(records), pin_vol = host_is_pinned(cost),
              pin_flags = host_is_pinned(flags);
-  const size_t o_cost = 0, o_rec = o_cost + (pin_cost ? 0 : (size_t)B * 8), o_vol = o_rec + (pin_rec ? 0 : rec_doubles * 8),
-               o_idx = o_vol + (cost && !pin_vol ? total * 8 : 0), o_meta = o_idx + (pin_idx ? 0 : (size_t)B * 4),
-               o_flags = o_meta + (pin_meta ? 0 : (size_t)B * 8), o_end = o_flags + (flags && !pin_flags ? total * 4 : 0);
+  const size_t o_win = 0, o_rec = o_win + ((w_bytes + 15) & ~(size_t)15), o_vol = o_rec + (pin_rec ? 0 : rec_doubles * 8),
+               o_flags = o_vol + (cost && !pin_vol ? total * 8 : 0), o_end = o_flags + (flags && !pin_flags ? total * 4 : 0);
   FISS_CUDA(h, h->h_out.ensure(o_end));
   char* ho = h->h_out.as<char>();
   const void* ego_src = ego;
@@ -621,26 +618,20 @@ static int32_t plan_common(fiss_handle* h, cudaStream_t st, const double* ego, i
   }
   if (rc != FISS_OK) return rc;
   rc = fiss_pick_winners_dev(h, stream, h->d_ego.as<double>(), B, h->d_end.as<double>(), C, p,
-                             h->d_cost.as<double>(), h->d_flags.as<uint32_t>(), h->d_best_idx.as<int32_t>(),
-                             h->d_best_cost.as<double>(), records ? h->d_records.as<double>() : nullptr,
-                             h->d_meta.as<int32_t>(), n_stride);
+                             h->d_cost.as<double>(), h->d_flags.as<uint32_t>(), d_bidx, d_bcost,
+                             records ? h->d_records.as<double>() : nullptr, d_bmeta, n_stride);
   if (rc != FISS_OK) return rc;
-  void* t_cost = pin_cost ? (void*)best_cost : (void*)(ho + o_cost);
-  void* t_idx = pin_idx ? (void*)best_idx : (void*)(ho + o_idx);
-  void* t_meta = pin_meta ? (void*)best_meta : (void*)(ho + o_meta);
   void* t_rec = pin_rec ? (void*)records : (void*)(ho + o_rec);
   void* t_vol = pin_vol ? (void*)cost : (void*)(ho + o_vol);
   void* t_flags = pin_flags ? (void*)flags : (void*)(ho + o_flags);
-  FISS_CUDA(h, cudaMemcpyAsync(t_cost, h->d_best_cost.p, (size_t)B * 8, cudaMemcpyDeviceToHost, st));
-  FISS_CUDA(h, cudaMemcpyAsync(t_idx, h->d_best_idx.p, (size_t)B * 4, cudaMemcpyDeviceToHost, st));
-  FISS_CUDA(h, cudaMemcpyAsync(t_meta, h->d_meta.p, (size_t)B * 8, cudaMemcpyDeviceToHost, st));
+  FISS_CUDA(h, cudaMemcpyAsync(ho + o_win, dw, w_bytes, cudaMemcpyDeviceToHost, st));
   if (records) FISS_CUDA(h, cudaMemcpyAsync(t_rec, h->d_records.p, rec_doubles * 8, cudaMemcpyDeviceToHost, st));
   if (cost) FISS_CUDA(h, cudaMemcpyAsync(t_vol, h->d_cost.p, total * 8, cudaMemcpyDeviceToHost, st));
   if (flags) FISS_CUDA(h, cudaMemcpyAsync(t_flags, h->d_flags.p, total * 4, cudaMemcpyDeviceToHost, st));
   FISS_CUDA(h, cudaStreamSynchronize(st));
-  if (!pin_cost) std::memcpy(best_cost, t_cost, (size_t)B * 8);
-  if (!pin_idx) std::memcpy(best_idx, t_idx, (size_t)B * 4);
-  if (best_meta && !pin_meta) std::memcpy(best_meta, t_meta, (size_t)B * 8);
+  std::memcpy(best_cost, ho + o_win + w_cost, (size_t)B * 8);
+  std::memcpy(best_idx, ho + o_win + w_idx, (size_t)B * 4);
+  if (best_meta) std::memcpy(best_meta, ho + o_win + w_meta, (size_t)B * 8);
   if (records && !pin_rec) std::memcpy(records, t_rec, rec_doubles * 8);
   if (cost && !pin_vol) std::memcpy(cost, t_vol, total * 8);
   if (flags && !pin_flags) std::memcpy(flags, t_flags, total * 4);
@@ -706,33 +697,39 @@ int32_t fiss_eval_end_states_host(fiss_handle* h, void* stream, const double* eg
   FISS_CUDA(h, cudaSetDevice(h->device));
   cudaStream_t st = (cudaStream_t)stream;
   const size_t rec_doubles = records ? (size_t)N * FISS_REC_ROWS * n_stride : 0;
-  FISS_CUDA(h, h->d_ego.ensure(48));
-  FISS_CUDA(h, h->d_cost.ensure((size_t)N * 8));
-  FISS_CUDA(h, h->d_flags.ensure((size_t)N * 4));
+  // one block in ([ego 48 B | end N x 32 B]) and one block out ([cost N x 8 | flags N x 4]): this call sits on the
+  // latency path of the FISS / FISS+ searches (a handful of end states per call), so copies are what it costs
+  const size_t in_bytes = 48 + (size_t)N * 32, out_bytes = (size_t)N * 12;
+  const size_t in_pad = (in_bytes + 15) & ~(size_t)15;
+  FISS_CUDA(h, h->d_es.ensure(in_pad + out_bytes));
+  char* d_in = h->d_es.as<char>();
+  char* d_out = d_in + in_pad;
+  double* d_ego = reinterpret_cast<double*>(d_in);
+  double* d_end = reinterpret_cast<double*>(d_in + 48);
+  double* d_cost = reinterpret_cast<double*>(d_out);
+  uint32_t* d_flags = reinterpret_cast<uint32_t*>(d_out + (size_t)N * 8);
   if (records) FISS_CUDA(h, h->d_records.ensure(rec_doubles * 8));
-  FISS_CUDA(h, h->h_in.ensure(48));
-  const size_t o_cost = 0, o_rec = (size_t)N * 8, o_flags = o_rec + rec_doubles * 8, o_end = o_flags + (size_t)N * 4;
-  FISS_CUDA(h, h->h_out.ensure(o_end));
+  FISS_CUDA(h, h->h_in.ensure(in_bytes));
+  const bool pin_rec = host_is_pinned(records);
+  const size_t o_rec = (out_bytes + 15) & ~(size_t)15;
+  FISS_CUDA(h, h->h_out.ensure(o_rec + (pin_rec ? 0 : rec_doubles * 8)));
   char* ho = h->h_out.as<char>();
   std::memcpy(h->h_in.p, ego6, 48);
-  FISS_CUDA(h, cudaMemcpyAsync(h->d_ego.p, h->h_in.p, 48, cudaMemcpyHostToDevice, st));
-  rc = upload_end_states(h, st, end, N);
-  if (rc != FISS_OK) return rc;
+  std::memcpy(h->h_in.as<char>() + 48, end, (size_t)N * 32);
+  FISS_CUDA(h, cudaMemcpyAsync(d_in, h->h_in.p, in_bytes, cudaMemcpyHostToDevice, st));
   if (records) {
-    rc = fiss_full_records_dev(h, stream, h->d_ego.as<double>(), h->d_end.as<double>(), nullptr, N, p,
-                               h->d_records.as<double>(), h->d_cost.as<double>(), h->d_flags.as<uint32_t>(), n_stride);
+    rc = fiss_full_records_dev(h, stream, d_ego, d_end, nullptr, N, p, h->d_records.as<double>(), d_cost, d_flags, n_stride);
   } else {
-    rc = fiss_eval_candidates_dev(h, stream, h->d_ego.as<double>(), 1, h->d_end.as<double>(), N, p,
-                                  h->d_cost.as<double>(), h->d_flags.as<uint32_t>(), nullptr, n_stride);
+    rc = fiss_eval_candidates_dev(h, stream, d_ego, 1, d_end, N, p, d_cost, d_flags, nullptr, n_stride);
   }
   if (rc != FISS_OK) return rc;
-  FISS_CUDA(h, cudaMemcpyAsync(ho + o_cost, h->d_cost.p, (size_t)N * 8, cudaMemcpyDeviceToHost, st));
-  FISS_CUDA(h, cudaMemcpyAsync(ho + o_flags, h->d_flags.p, (size_t)N * 4, cudaMemcpyDeviceToHost, st));
-  if (records) FISS_CUDA(h, cudaMemcpyAsync(ho + o_rec, h->d_records.p, rec_doubles * 8, cudaMemcpyDeviceToHost, st));
+  FISS_CUDA(h, cudaMemcpyAsync(ho, d_out, out_bytes, cudaMemcpyDeviceToHost, st));
+  void* t_rec = pin_rec ? (void*)records : (void*)(ho + o_rec);
+  if (records) FISS_CUDA(h, cudaMemcpyAsync(t_rec, h->d_records.p, rec_doubles * 8, cudaMemcpyDeviceToHost, st));
   FISS_CUDA(h, cudaStreamSynchronize(st));
-  std::memcpy(cost, ho + o_cost, (size_t)N * 8);
-  std::memcpy(flags, ho + o_flags, (size_t)N * 4);
-  if (records) std::memcpy(records, ho + o_rec, rec_doubles * 8);
+  std::memcpy(cost, ho, (size_t)N * 8);
+  std::memcpy(flags, ho + (size_t)N * 8, (size_t)N * 4);
+  if (records && !pin_rec) std::memcpy(records, t_rec, rec_doubles * 8);
   return FISS_OK;
 }
 

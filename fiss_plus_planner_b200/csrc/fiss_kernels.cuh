@@ -485,7 +485,9 @@ __device__ __forceinline__ bool better(double c, int i, double bc, int bi) {
 __global__ void __launch_bounds__(kPickThreads) fiss_pick_kernel(const double* __restrict__ cost,
                                                                  const uint32_t* __restrict__ flags, int C,
                                                                  int32_t* __restrict__ best_idx,
-                                                                 double* __restrict__ best_cost) {
+                                                                 double* __restrict__ best_cost,
+                                                                 const double* __restrict__ end,
+                                                                 int32_t* __restrict__ meta) {
   __shared__ double s_cost[kPickThreads / 32];
   __shared__ int s_idx[kPickThreads / 32];
   const int b = blockIdx.x;
@@ -524,21 +526,10 @@ __global__ void __launch_bounds__(kPickThreads) fiss_pick_kernel(const double* _
     }
     best_idx[b] = bi;
     best_cost[b] = bi >= 0 ? bc : CUDART_INF;
-  }
-}
-
-// (n, n') of the winners, for the host to cut the ragged record rows
-__global__ void fiss_meta_kernel(const int32_t* __restrict__ best_idx, const double* __restrict__ end,
-                                 const uint32_t* __restrict__ flags, int B, int C, int32_t* __restrict__ meta) {
-  const int b = blockIdx.x * blockDim.x + threadIdx.x;
-  if (b >= B) return;
-  const int c = best_idx[b];
-  if (c < 0) {
-    meta[2 * b] = 0;
-    meta[2 * b + 1] = 0;
-  } else {
-    meta[2 * b] = (int)end[4 * (int64_t)c + 3];
-    meta[2 * b + 1] = (int)((flags[(int64_t)b * C + c] >> FISS_FLAG_NCART_SHIFT) & FISS_FLAG_NCART_MASK);
+    if (meta) {  // (n, n') of the winner, for the host to cut the ragged record rows
+      meta[2 * b] = bi >= 0 ? (int)end[4 * (int64_t)bi + 3] : 0;
+      meta[2 * b + 1] = bi >= 0 ? (int)((pf[bi] >> FISS_FLAG_NCART_SHIFT) & FISS_FLAG_NCART_MASK) : 0;
+    }
   }
 }
 

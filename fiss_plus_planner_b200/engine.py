@@ -18,7 +18,9 @@ from fiss_plus_planner_b200._shim import FissError, FissGrid, FissParams
 def end_state_table(d, v, T, tick: float) -> np.ndarray:
     """``[C, 4] = (d_end, v_end, T, n)`` with ``n = len(np.arange(0, T, tick))``."""
     d, v, T = np.broadcast_arrays(np.asarray(d, np.float64), np.asarray(v, np.float64), np.asarray(T, np.float64))
-    n = np.array([_shim.arange_len(t, tick) for t in T.ravel()], dtype=np.float64)
+    # len(np.arange(0, T, tick)) = ceil((T - 0) / tick) evaluated in float64 (SURVEY A.1) -- the same two IEEE
+    # operations as fiss_arange_len in the C ABI (tests/test_abi_exports.py pins both against NumPy)
+    n = np.ceil((T.ravel() - 0.0) / float(tick))
     return np.ascontiguousarray(np.column_stack((d.ravel(), v.ravel(), T.ravel(), n)))
 
 

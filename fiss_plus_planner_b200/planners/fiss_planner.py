@@ -80,8 +80,13 @@ class FissPlanner(FrenetOptimalPlanner):
         evaluated with the reference's operation order so that the ``<=`` scan of
         ``find_initial_guess`` sees the same ties."""
         st = self.settings
-        table, ds, vs, ts, res = fiss_lattice(st, self.vehicle.w)
-        self._fgrid = fiss_grid(st, self.vehicle.w)      # same points, as axes + [i_d][j_v][k_t] numbering
+        key = (st.max_road_width, self.vehicle.w, st.num_width, st.min_t, st.max_t, st.num_t, st.lowest_speed,
+               st.highest_speed, st.num_speed, st.tick_t)
+        if key != getattr(self, "_fiss_lattice_key", None):   # the lattice only moves when the settings do
+            self._fiss_lattice = fiss_lattice(st, self.vehicle.w)
+            self._fgrid = fiss_grid(st, self.vehicle.w)      # same points, as axes + [i_d][j_v][k_t] numbering
+            self._fiss_lattice_key = key
+        table, ds, vs, ts, res = self._fiss_lattice
         sw = st.max_road_width - self.vehicle.w + 0.3
         left, right = -sw / 2, sw / 2
         self.sampling_min[:] = (left, st.lowest_speed, st.min_t)
