@@ -20,7 +20,7 @@ MAT_ROWS = 5
 
 EXPORTS = (
     "fiss_create", "fiss_destroy", "fiss_last_error", "fiss_abi_version", "fiss_arange_len",
-    "fiss_set_spline", "fiss_set_obstacles", "fiss_set_obstacles_waymo",
+    "fiss_set_spline", "fiss_fit_splines_host", "fiss_frame_samples_host", "fiss_set_obstacles", "fiss_set_obstacles_waymo",
     "fiss_eval_candidates_dev", "fiss_eval_grid_dev", "fiss_pick_winners_dev", "fiss_full_records_dev",
     "fiss_plan_lattice_host", "fiss_plan_grid_host", "fiss_eval_end_states_host", "fiss_launch_count",
 )
@@ -78,6 +78,8 @@ def load():
         "fiss_abi_version": (i32, []),
         "fiss_arange_len": (i32, [f64, f64]),
         "fiss_set_spline": (i32, [vp, vp, vp, i32]),
+        "fiss_fit_splines_host": (i32, [vp, vp, vp, i32, i32, vp, i32]),
+        "fiss_frame_samples_host": (i32, [vp, vp, f64, i32, vp]),
         "fiss_set_obstacles": (i32, [vp, vp, vp, vp, vp, i32, i32, i32]),
         "fiss_set_obstacles_waymo": (i32, [vp, vp, vp, vp, i32, i32, i32]),
         "fiss_eval_candidates_dev": (i32, [vp, vp, vp, i32, vp, i32, pp, vp, vp, vp, i32]),

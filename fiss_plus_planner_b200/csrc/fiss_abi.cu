@@ -12,6 +12,7 @@
 #include <vector>
 
 #include "fiss_grid_kernel.cuh"
+#include "fiss_spline_kernels.cuh"
 
 namespace {
 
@@ -83,6 +84,7 @@ struct fiss_handle {
   std::vector<double> end_cache;
   // product lattice (fiss_grid): device axes [4][kAxisMax] + the expanded [C][4] table in d_end
   DevBuf d_axes;
+  DevBuf d_fit_in, d_fit_out;  // fiss_fit_splines_host / fiss_frame_samples_host
   std::vector<double> axes_cache;
   int grid_n_max = 0;
   size_t smem_attr[8] = {0, 0, 0, 0, 0, 0, 0, 0};
@@ -365,7 +367,7 @@ int32_t fiss_destroy(fiss_handle* h) {
   cudaSetDevice(h->device);
   for (DevBuf* b : {&h->spline, &h->obs_tab, &h->obs_const, &h->obs_raw, &h->obs_lw, &h->obs_valid, &h->d_ego,
                     &h->d_end, &h->d_cost, &h->d_flags, &h->d_best_idx, &h->d_best_cost, &h->d_meta, &h->d_records,
-                    &h->d_es, &h->d_axes})
+                    &h->d_es, &h->d_axes, &h->d_fit_in, &h->d_fit_out})
     b->release();
   h->h_in.release();
   h->h_out.release();
@@ -397,6 +399,67 @@ int32_t fiss_set_spline(fiss_handle* h, void* stream, const double* table, int32
   FISS_CUDA(h, cudaStreamSynchronize(st));
   h->K = K;
   h->Kp = Kp;
+  return FISS_OK;
+}
+
+int32_t fiss_fit_splines_host(fiss_handle* h, void* stream, const double* xy, int32_t L, int32_t K, double* tables,
+                              int32_t install_lane) {
+  if (!h) return FISS_ERR_INVALID;
+  if (!xy || L < 1 || K < 2) return fail(h, FISS_ERR_INVALID, "fit_splines: need L >= 1 lanes of K >= 2 way points");
+  if (install_lane >= L) return fail(h, FISS_ERR_INVALID, "fit_splines: install_lane out of range");
+  cudaStream_t st = (cudaStream_t)stream;
+  FISS_CUDA(h, cudaSetDevice(h->device));
+  const int Kp = (K + 1) & ~1;
+  const size_t smem = (size_t)6 * Kp * 8;
+  if (smem > kSmemLimit) return fail(h, FISS_ERR_CAPACITY, "fit_splines: more way points than 227 KB of shared memory hold");
+  const size_t in_bytes = (size_t)L * K * 2 * 8, tab_doubles = (size_t)L * 9 * Kp;
+  FISS_CUDA(h, h->h_in.ensure(in_bytes));
+  std::memcpy(h->h_in.p, xy, in_bytes);
+  FISS_CUDA(h, h->d_fit_in.ensure(in_bytes));
+  FISS_CUDA(h, h->d_fit_out.ensure(tab_doubles * 8));
+  FISS_CUDA(h, cudaMemcpyAsync(h->d_fit_in.p, h->h_in.p, in_bytes, cudaMemcpyHostToDevice, st));
+  if (smem > 48 * 1024 && smem > h->smem_attr[6]) {
+    FISS_CUDA(h, cudaFuncSetAttribute(fiss::fiss_spline_fit_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemLimit));
+    h->smem_attr[6] = kSmemLimit;
+  }
+  fiss::fiss_spline_fit_kernel<<<L, fiss::kFitThreads, smem, st>>>(h->d_fit_in.as<double>(), K, Kp, h->d_fit_out.as<double>());
+  h->launches++;
+  FISS_CUDA(h, cudaGetLastError());
+  if (install_lane >= 0) {
+    FISS_CUDA(h, h->spline.ensure((size_t)9 * Kp * 8));
+    FISS_CUDA(h, cudaMemcpyAsync(h->spline.p, h->d_fit_out.as<double>() + (size_t)install_lane * 9 * Kp, (size_t)9 * Kp * 8,
+                                 cudaMemcpyDeviceToDevice, st));
+    h->K = K;
+    h->Kp = Kp;
+  }
+  if (tables) {
+    FISS_CUDA(h, h->h_out.ensure(tab_doubles * 8));
+    FISS_CUDA(h, cudaMemcpyAsync(h->h_out.p, h->d_fit_out.p, tab_doubles * 8, cudaMemcpyDeviceToHost, st));
+  }
+  FISS_CUDA(h, cudaStreamSynchronize(st));
+  if (tables) {
+    const double* src = h->h_out.as<double>();
+    for (int64_t r = 0; r < (int64_t)L * 9; ++r) std::memcpy(tables + r * K, src + r * Kp, (size_t)K * 8);
+  }
+  return FISS_OK;
+}
+
+int32_t fiss_frame_samples_host(fiss_handle* h, void* stream, double step, int32_t m, double* ref) {
+  if (!h) return FISS_ERR_INVALID;
+  if (!ref || m < 1 || !(step > 0.0)) return fail(h, FISS_ERR_INVALID, "frame_samples: bad arguments");
+  if (h->K < 2) return fail(h, FISS_ERR_STATE, "no reference line: call fiss_set_spline / fiss_fit_splines_host first");
+  cudaStream_t st = (cudaStream_t)stream;
+  FISS_CUDA(h, cudaSetDevice(h->device));
+  const size_t bytes = (size_t)m * 4 * 8;
+  FISS_CUDA(h, h->d_fit_out.ensure(bytes));
+  FISS_CUDA(h, h->h_out.ensure(bytes));
+  fiss::fiss_frame_samples_kernel<<<(m + 127) / 128, 128, 0, st>>>(h->spline.as<double>(), h->K, h->Kp, step, m,
+                                                                  h->d_fit_out.as<double>());
+  h->launches++;
+  FISS_CUDA(h, cudaGetLastError());
+  FISS_CUDA(h, cudaMemcpyAsync(h->h_out.p, h->d_fit_out.p, bytes, cudaMemcpyDeviceToHost, st));
+  FISS_CUDA(h, cudaStreamSynchronize(st));
+  std::memcpy(ref, h->h_out.p, bytes);
   return FISS_OK;
 }
 

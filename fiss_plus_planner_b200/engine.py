@@ -171,6 +171,29 @@ class FissEngine:
         self._check(self._lib.fiss_set_spline(self._h, self._stream(stream), _shim.ptr(table), table.shape[1]),
                     "fiss_set_spline")
 
+    def fit_splines(self, lanes, install: int = 0, stream=None) -> np.ndarray:
+        """Natural cubic splines of ``lanes [L, K, 2]`` (or one lane ``[K, 2]``) fitted on the device (Thomas
+        recurrence, one CTA per lane).  Returns the coefficient tables ``[L, 9, K]`` (the layout of
+        ``CubicSpline2D.device_table()``); lane ``install`` (>= 0) becomes the engine's reference line."""
+        lanes = np.ascontiguousarray(lanes, dtype=np.float64)
+        if lanes.ndim == 2:
+            lanes = lanes[None]
+        n_lanes, k, two = lanes.shape
+        assert two == 2 and k >= 2
+        tables = np.empty((n_lanes, 9, k), np.float64)
+        self._check(self._lib.fiss_fit_splines_host(self._h, self._stream(stream), _shim.ptr(lanes), n_lanes, k,
+                                                    _shim.ptr(tables), int(install)), "fiss_fit_splines_host")
+        return tables
+
+    def frame_samples(self, s_end: float, step: float = 0.1, stream=None) -> np.ndarray:
+        """``[m, 4] = (x, y, yaw, curvature)`` of the installed reference line at ``np.arange(0, s_end, step)``
+        (generate_frenet_frame's polyline, frenet_optimal_planner.py:274-278), evaluated on the device."""
+        m = _shim.arange_len(s_end, step)
+        ref = np.empty((m, 4), np.float64)
+        self._check(self._lib.fiss_frame_samples_host(self._h, self._stream(stream), float(step), m, _shim.ptr(ref)),
+                    "fiss_frame_samples_host")
+        return ref
+
     def set_obstacles(self, xyth, lw, valid, final_time_step: int, stream=None):
         if xyth is None or len(lw) == 0:
             self._check(self._lib.fiss_set_obstacles(self._h, self._stream(stream), None, None, None, 0, 0,

@@ -88,7 +88,33 @@ class CubicSpline1D:
         return out
 
 
+class _TableSpline1D(CubicSpline1D):
+    """``CubicSpline1D`` interface over coefficient rows that were fitted elsewhere (the device)."""
+
+    def __init__(self, knots, rows):
+        k = len(knots)
+        self.x = [float(v) for v in knots]
+        self.y = [float(v) for v in rows[0]]
+        self.nx = k
+        self._knots = np.asarray(knots, dtype=np.float64)
+        self.a = [float(v) for v in rows[0]]
+        self.b = [float(v) for v in rows[1][:k - 1]]
+        self.c = np.array(rows[2], dtype=np.float64)
+        self.d = [float(v) for v in rows[3][:k - 1]]
+
+
 class CubicSpline2D:
+    @classmethod
+    def from_device_table(cls, table: np.ndarray) -> "CubicSpline2D":
+        """Host view of a ``[9, K]`` table produced by ``FissEngine.fit_splines`` (same ``calc_*`` interface)."""
+        table = np.asarray(table, dtype=np.float64)
+        self = cls.__new__(cls)
+        self.s = [float(v) for v in table[0]]
+        self.ds = np.diff(table[0])
+        self.sx = _TableSpline1D(table[0], table[1:5])
+        self.sy = _TableSpline1D(table[0], table[5:9])
+        return self
+
     def __init__(self, x, y):
         dx = np.diff(x)
         dy = np.diff(y)

@@ -217,10 +217,20 @@ class FrenetOptimalPlanner(object):
         return FrenetTrajectory().fill_from_device_record(rec, int(meta[0]), int(meta[1]), float(cost))
 
     # -- reference API ---------------------------------------------------------------------------
-    def generate_frenet_frame(self, centerline_pts: np.ndarray):
-        """Spline fit on the host (float64, the reference's own dense solve), table upload, and the
-        0.1 m polyline ``[m, 4] = (x, y, yaw, curvature)`` that ``FrenetState.from_state`` consumes
-        (frenet_optimal_planner.py:272-278)."""
+    def generate_frenet_frame(self, centerline_pts: np.ndarray, fit: str = "host"):
+        """Reference-line set-up (frenet_optimal_planner.py:272-278): spline through the centre line, table upload,
+        and the 0.1 m polyline ``[m, 4] = (x, y, yaw, curvature)`` that ``FrenetState.from_state`` consumes.
+
+        ``fit="host"`` (default): the reference's own dense float64 solve on the host -- coefficients identical to
+        the reference's, which the bit-exact mask parity rests on.  ``fit="device"``: the Thomas-recurrence fit and
+        the resampling run on the GPU (``fiss_fit_splines_host`` / ``fiss_frame_samples_host``); equal to the host
+        path to rounding (~1e-15 relative)."""
+        if fit == "device":
+            table = self.engine.fit_splines(np.asarray(centerline_pts, dtype=np.float64)[:, :2], install=0)[0]
+            self.cubic_spline = CubicSpline2D.from_device_table(table)
+            return self.cubic_spline, self.engine.frame_samples(self.cubic_spline.s[-1], 0.1)
+        if fit != "host":
+            raise ValueError("fit must be 'host' or 'device'")
         self.cubic_spline = CubicSpline2D(centerline_pts[:, 0], centerline_pts[:, 1])
         self.engine.set_spline(self.cubic_spline.device_table())
         s = np.arange(0, self.cubic_spline.s[-1], 0.1)

@@ -108,6 +108,20 @@ int32_t fiss_arange_len(double T, double tick);
  * Replaces the per-step CubicSpline2D.calc_position / calc_yaw calls (:170-190,214-232). */
 int32_t fiss_set_spline(fiss_handle* h, void* stream, const double* table, int32_t K);
 
+/* Fit the natural cubic splines of L centre lines ON THE DEVICE: xy [L][K][2] way points ->
+ * arc-length knots (np.cumsum of segment lengths) and the a, b, c, d rows of x(s), y(s) -- CubicSpline2D.__init__ /
+ * CubicSpline1D.__init__ (cubic_spline.py:19-43,118-142,157-168), with the dense K x K np.linalg.solve replaced by
+ * the tridiagonal (Thomas) recurrence, one CTA per lane.  tables [L][9][K] (host, may be NULL) receives the
+ * coefficient tables; install_lane >= 0 makes that lane the handle's reference line (as fiss_set_spline would),
+ * -1 installs nothing.  Agrees with the host fit to rounding (~1e-15 relative), not bit for bit. */
+int32_t fiss_fit_splines_host(fiss_handle* h, void* stream, const double* xy, int32_t L, int32_t K, double* tables,
+                              int32_t install_lane);
+
+/* The 0.1 m polyline of generate_frenet_frame (frenet_optimal_planner.py:274-278): ref [m][4] = (x, y, yaw,
+ * curvature) of the handle's reference line at s_i = i * step, i < m (CubicSpline2D.calc_position / calc_yaw /
+ * calc_curvature, cubic_spline.py:170-232); rows with s_i beyond the last knot are NaN. */
+int32_t fiss_frame_samples_host(fiss_handle* h, void* stream, double step, int32_t m, double* ref);
+
 /* Dense obstacle predictions: xyth [M][T_obs][3] = (x, y, orientation) at absolute time step t,
  * lw [M][2] = rectangle (length, width), valid [M][T_obs] != 0 where obstacle.state_at_time(t)
  * is not None, final_time_step = obstacles[0].prediction.final_time_step
