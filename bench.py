@@ -43,6 +43,28 @@ LATTICE = (9, 6, 5)
 MIN_T, MAX_T = 4.0, 5.0
 NUM_OBS = 32
 BATCH_PER_GPU = 512
+SCENE = "cfg4_batch4096_32obs"
+# --workload: the other BASELINE configs as side measurements (the default, and the line the driver reads, is cfg4)
+WORKLOADS = {
+    "cfg4": dict(scene="cfg4_batch4096_32obs", lattice=(9, 6, 5), t=(4.0, 5.0), obstacles=32, batch=512,
+                 text="cfg4 shard: %d ego states/GPU x 9x6x5 lattice (270 candidates) x n<=50 steps x %d obstacles "
+                      "(north_star target config; configs[3] = 4096 states on 8 GPUs)"),
+    "cfg3": dict(scene="cfg3_64obs", lattice=(9, 6, 5), t=(4.0, 5.0), obstacles=64, batch=512,
+                 text="cfg3 (collision-check bound): %d ego states/GPU x 9x6x5 lattice x n<=50 steps x %d obstacles"),
+    "cfg5": dict(scene="cfg5_fine_lattice", lattice=(33, 17, 9), t=(8.0, 10.0), obstacles=32, batch=32,
+                 text="cfg5 (fine lattice): %d ego states/GPU x 33x17x9 lattice (5049 candidates) x n<=100 steps x %d obstacles"),
+}
+
+
+def select_workload(name: str, batch_per_gpu):
+    global LATTICE, MIN_T, MAX_T, NUM_OBS, BATCH_PER_GPU, SCENE, WORKLOAD_TEXT
+    w = WORKLOADS[name]
+    LATTICE, (MIN_T, MAX_T), NUM_OBS, SCENE, WORKLOAD_TEXT = w["lattice"], w["t"], w["obstacles"], w["scene"], w["text"]
+    BATCH_PER_GPU = w["batch"]
+    return BATCH_PER_GPU if batch_per_gpu is None else batch_per_gpu
+
+
+WORKLOAD_TEXT = WORKLOADS["cfg4"]["text"]
 METRIC = "candidate_trajectories_per_sec"
 UNIT = "candidates/s"
 
@@ -50,18 +72,19 @@ UNIT = "candidates/s"
 # ------------------------------------------------------------------------------------------------ scene
 def make_workload(n_gpus: int, batch_per_gpu: int):
     from fiss_plus_planner_b200 import synthetic as syn
-    sc = syn.make_scene("cfg4_batch4096_32obs", batch=batch_per_gpu * n_gpus, num_obstacles=NUM_OBS)
+    sc = syn.make_scene(SCENE, batch=batch_per_gpu * n_gpus, num_obstacles=NUM_OBS)
     return sc
 
 
 def config_dict(n_gpus, batch_per_gpu):
     return {
-        "workload": "cfg4 shard: %d ego states/GPU x 9x6x5 lattice (270 candidates) x n<=50 steps x %d obstacles "
-                    "(north_star target config; configs[3] = 4096 states on 8 GPUs)" % (batch_per_gpu, NUM_OBS),
-        "lattice": list(LATTICE), "steps_per_candidate": "40..50 (T in [4,5] s, tick 0.1 s)",
+        "workload": WORKLOAD_TEXT % (batch_per_gpu, NUM_OBS),
+        "lattice": list(LATTICE), "steps_per_candidate": "%d..%d (T in [%g,%g] s, tick 0.1 s)" % (
+            int(np.ceil(MIN_T / 0.1)), int(np.ceil(MAX_T / 0.1)), MIN_T, MAX_T),
         "obstacles": NUM_OBS, "batch_per_gpu": batch_per_gpu, "global_batch": batch_per_gpu * n_gpus,
         "parallelism": "problems sharded across %d GPU(s), no data-path collective" % n_gpus,
-        "l2": "per-step output (276 MB/GPU in materialisation mode) exceeds the 126 MB L2",
+        "l2": "per-step output (%d MB/GPU in materialisation mode) exceeds the 126 MB L2" % round(
+            5 * batch_per_gpu * LATTICE[0] * LATTICE[1] * LATTICE[2] * int(np.ceil(MAX_T / 0.1)) * 8 / 1e6),
     }
 
 
@@ -96,9 +119,9 @@ def cpu_port_rate(sc, steps: int, warmup: int, budget_s: float):
     total = float(np.sum(times))
     return dict(value=n_cand * len(times) / total, steps_done=len(times), ms_per_step=1e3 * total / len(times),
                 cores=workers,
-                sample="%d step(s); each = one ego state's 270-candidate lattice (n<=50, %d obstacles) split over %d "
+                sample="%d step(s); each = one ego state's %d-candidate lattice (n<=%d, %d obstacles) split over %d "
                        "processes; Python port of the reference loops, NumPy SAT in place of shapely/GEOS"
-                       % (len(times), NUM_OBS, workers))
+                       % (len(times), n_cand, int(np.ceil(MAX_T / 0.1)), NUM_OBS, workers))
 
 
 # ------------------------------------------------------------------------------------------------ clocks
@@ -413,7 +436,7 @@ def run_ours(args):
         # DRAM bytes per launch of the same kernel / workload from the committed `ncu --set full` capture
         traffic, traffic_src = None, None
         tpath = os.path.join(ROOT, "profiles", "traffic.json")
-        if os.path.exists(tpath) and bpg == BATCH_PER_GPU:
+        if os.path.exists(tpath) and bpg == BATCH_PER_GPU and args.workload == "cfg4":
             tj = json.load(open(tpath))
             traffic, traffic_src = tj["dram_bytes_per_launch"], tj["source"]
         achieved = alg / (kern_ms * 1e-3) / 1e9
@@ -485,12 +508,14 @@ def main():
     ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--batch-per-gpu", type=int, default=BATCH_PER_GPU)
+    ap.add_argument("--batch-per-gpu", type=int, default=None)
+    ap.add_argument("--workload", default="cfg4", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-closed-loop", action="store_true", help="skip the config-1 closed-loop latency section")
     ap.add_argument("--cpu-steps", type=int, default=150,
                     help="CPU-baseline sample: lattices evaluated by the oracle port (150 x ~80 ms = ~12 s of host time)")
     args = ap.parse_args()
+    args.batch_per_gpu = select_workload(args.workload, args.batch_per_gpu)
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":
         run_reference(args)

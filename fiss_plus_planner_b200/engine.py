@@ -179,7 +179,7 @@ class FissEngine:
         if lanes.ndim == 2:
             lanes = lanes[None]
         n_lanes, k, two = lanes.shape
-        assert two == 2 and k >= 2
+        assert two == 2, "lanes must be [L, K, 2]"
         tables = np.empty((n_lanes, 9, k), np.float64)
         self._check(self._lib.fiss_fit_splines_host(self._h, self._stream(stream), _shim.ptr(lanes), n_lanes, k,
                                                     _shim.ptr(tables), int(install)), "fiss_fit_splines_host")
