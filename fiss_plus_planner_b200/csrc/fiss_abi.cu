@@ -330,6 +330,16 @@ extern "C" {
 
 int32_t fiss_abi_version(void) { return 1; }
 
+#ifdef FISS_PHASE_TIMING
+// debug builds only (tools/phase_timing.py): read and reset the per-stage cycle counters of the lattice kernel
+int32_t fiss_debug_phase_cycles(long long* out) {
+  long long zero[16] = {0};
+  if (cudaMemcpyFromSymbol(out, g_fiss_phase, 8 * sizeof(long long)) != cudaSuccess) return FISS_ERR_CUDA;
+  if (cudaMemcpyToSymbol(g_fiss_phase, zero, sizeof(zero)) != cudaSuccess) return FISS_ERR_CUDA;
+  return FISS_OK;
+}
+#endif
+
 int32_t fiss_arange_len(double T, double tick) {
   if (!(tick > 0.0) || !(T > 0.0)) return 0;
   const double len = std::ceil((T - 0.0) / tick);  // NumPy: ceil((stop - start) / step) in double

@@ -34,6 +34,14 @@
 #include "fiss_kernels.cuh"
 #include "fiss_math.cuh"
 
+#ifdef FISS_PHASE_TIMING
+// debug build only (tools/phase_timing.py): thread 0 of every CTA accumulates the cycles between stage boundaries
+#define FISS_PHASE(k) do { if (threadIdx.x == 0) { const long long now_ = clock64(); phase_acc[k] += now_ - phase_t; phase_t = now_; } } while (0)
+__device__ long long g_fiss_phase[16];
+#else
+#define FISS_PHASE(k) do { } while (0)
+#endif
+
 namespace fiss {
 
 #ifndef FISS_GRID_WARPS
@@ -112,6 +120,16 @@ __host__ __device__ inline GridLayout grid_layout(int Kp, int Mp, int E_stage, i
   return L;
 }
 
+// Doubles as unsigned 64-bit keys whose integer order is the numeric order (for shared-memory atomicMin / atomicMax).
+__device__ __forceinline__ unsigned long long order_key(double v) {
+  const long long b = __double_as_longlong(v);
+  return (unsigned long long)(b ^ ((b >> 63) | (long long)0x8000000000000000ull));
+}
+__device__ __forceinline__ double order_value(unsigned long long k) {
+  const long long b = (long long)k;
+  return __longlong_as_double(b ^ (((b >> 63) ^ -1ll) | (long long)0x8000000000000000ull));
+}
+
 // Squared distance, one expression for the box test and the per-row test of stage A' (so that rounding is monotone:
 // |bx| <= |dx| and |by| <= |dy| imply near2(bx, by) <= near2(dx, dy) bit for bit).
 __device__ __forceinline__ double near2(double dx, double dy) { return fma(dx, dx, dy * dy); }
@@ -130,13 +148,18 @@ __device__ __forceinline__ void grid_pos(const double2* __restrict__ P2, const d
 // kYaw: heading / curvature are needed (materialisation and/or the optional curvature mask).
 template <bool kYaw>
 __global__ void __launch_bounds__(kGridThreads, kGridMinCtas) fiss_grid_kernel(const GridArgs a) {
+#ifdef FISS_PHASE_TIMING
+  long long phase_acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  long long phase_t = clock64();
+#endif
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const GridLayout L = grid_layout(a.Kp, a.Mp, a.E_stage, a.nv, a.d_chunk, a.n_pad, a.e_pad, a.words);
   uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw);  // [0] spline, [1] obstacles
   double* sp = reinterpret_cast<double*>(smem_raw + L.spline);
   double* oc = reinterpret_cast<double*>(smem_raw + L.oc);
   double* obs_s = reinterpret_cast<double*>(smem_raw + L.obs);
-  double* bbox = reinterpret_cast<double*>(smem_raw + L.bbox);  // [e_pad][4]: x_min, x_max, y_min, y_max of the frame points
+  // [e_pad][4]: x_min, x_max, y_min, y_max of the frame points of the rows that check a step, as order-preserving keys
+  unsigned long long* bbox_key = reinterpret_cast<unsigned long long*>(smem_raw + L.bbox);
   double* ax = reinterpret_cast<double*>(smem_raw + L.axes);
   double* lon = reinterpret_cast<double*>(smem_raw + L.lon);
   double* lat = reinterpret_cast<double*>(smem_raw + L.lat);
@@ -193,6 +216,7 @@ __global__ void __launch_bounds__(kGridThreads, kGridMinCtas) fiss_grid_kernel(c
   mbar_wait(&bar[0], 0);
   mbar_wait(&bar[1], 0);
   __syncthreads();
+  FISS_PHASE(0);
 
   const double* obs = a.E_stage > 0 ? obs_s : a.obs_tab;
   const int obs_row0 = a.E_stage > 0 ? 0 : p.time_step_now;
@@ -226,12 +250,17 @@ __global__ void __launch_bounds__(kGridThreads, kGridMinCtas) fiss_grid_kernel(c
       *n_near = 0u;
     }
     for (int q = threadIdx.x; q < n_cand; q += blockDim.x) cflags[q] = 0u;
+    // stage A' state: empty boxes (+inf, -inf: infinitely far from everything), clear masks and list marks
+    for (int q = threadIdx.x; q < 4 * e_pad; q += blockDim.x) bbox_key[q] = order_key((q & 1) ? -CUDART_INF : CUDART_INF);
+    for (int q = threadIdx.x; q < nv * e_pad; q += blockDim.x) listed[q] = 0u;
+    for (int q = threadIdx.x; q < nv * e_pad * words; q += blockDim.x) masks[q] = 0u;
     const double T = ax[2 * kAxisMax + k];
     const int n = (int)ax[3 * kAxisMax + k];
     const double* ego = a.ego + 6 * (int64_t)b;
     const double s0 = ego[0], v0 = ego[1], a0 = ego[2], d0 = ego[3], dv0 = ego[4], da0 = ego[5];
     const double T2 = T * T, T3 = T2 * T;
     __syncthreads();
+    FISS_PHASE(1);
 
     // ---- stage A: one warp per row
     for (int task = warp; task < nv + rows_i; task += wpc) {
@@ -248,39 +277,72 @@ __global__ void __launch_bounds__(kGridThreads, kGridMinCtas) fiss_grid_kernel(c
         unsigned viol = 0;
         int first_bad = n;
         const int base = j * n_pad;
-        for (int m = lane; m < n; m += 32) {
-          const double t = m * p.tick_t;  // np.arange: start + m*step
-          const double t2 = t * t, t3 = t2 * t, t4 = t3 * t;
-          const double s = s0 + v0 * t + qa2 * t2 + qa3 * t3 + qa4 * t4;
-          const double s_d = v0 + 2.0 * qa2 * t + 3.0 * qa3 * t2 + 4.0 * qa4 * t3;
-          const double s_dd = 2.0 * qa2 + 6.0 * qa3 * t + 12.0 * qa4 * t2;
-          const double s_ddd = 6.0 * qa3 + 24.0 * qa4 * t;
-          const double dv = s_d - p.target_speed;
-          acc += p.w_speed * (dv * dv) + p.w_accel * (s_dd * s_dd) + p.w_jerk * (s_ddd * s_ddd);  // cost_function.py:43-46
-          if (s_d > p.max_speed) viol |= FISS_FLAG_SPEED;         // frenet_optimal_planner.py:152
-          if (fabs(s_dd) > p.max_accel) viol |= FISS_FLAG_ACCEL;  // :155
-          double px, py, tx, ty;
-          if (spline_frame(sp, a.K, a.Kp, a.search_iters, s, px, py, tx, ty)) {
-            const double r = rsqrt(tx * tx + ty * ty);
-            P2[base + m] = make_double2(px, py);
-            U2[base + m] = make_double2(tx * r, ty * r);
+        // Two time steps per lane (m and m + 32) in lockstep: two independent dependency chains through the
+        // polynomials, the segment search and the frame -- a row is one warp's serial work, so its latency is the
+        // stage's.  The accumulation order (m, then m + 32, then m + 64 ...) is the one-step-per-pass order.
+        for (int m0 = lane; m0 < n; m0 += 64) {
+          const int m1 = m0 + 32;
+          const bool has1 = m1 < n;
+          const double tA = m0 * p.tick_t, tB = m1 * p.tick_t;  // np.arange: start + m*step
+          const double tA2 = tA * tA, tA3 = tA2 * tA, tA4 = tA3 * tA;
+          const double tB2 = tB * tB, tB3 = tB2 * tB, tB4 = tB3 * tB;
+          const double sA = s0 + v0 * tA + qa2 * tA2 + qa3 * tA3 + qa4 * tA4;
+          const double sB = s0 + v0 * tB + qa2 * tB2 + qa3 * tB3 + qa4 * tB4;
+          const double sdA = v0 + 2.0 * qa2 * tA + 3.0 * qa3 * tA2 + 4.0 * qa4 * tA3;
+          const double sdB = v0 + 2.0 * qa2 * tB + 3.0 * qa3 * tB2 + 4.0 * qa4 * tB3;
+          const double sddA = 2.0 * qa2 + 6.0 * qa3 * tA + 12.0 * qa4 * tA2;
+          const double sddB = 2.0 * qa2 + 6.0 * qa3 * tB + 12.0 * qa4 * tB2;
+          const double sdddA = 6.0 * qa3 + 24.0 * qa4 * tA;
+          const double sdddB = 6.0 * qa3 + 24.0 * qa4 * tB;
+          const double dvA = sdA - p.target_speed, dvB = sdB - p.target_speed;
+          acc += p.w_speed * (dvA * dvA) + p.w_accel * (sddA * sddA) + p.w_jerk * (sdddA * sdddA);  // cost_function.py:43-46
+          if (has1) acc += p.w_speed * (dvB * dvB) + p.w_accel * (sddB * sddB) + p.w_jerk * (sdddB * sdddB);
+          if (sdA > p.max_speed || (has1 && sdB > p.max_speed)) viol |= FISS_FLAG_SPEED;               // frenet_optimal_planner.py:152
+          if (fabs(sddA) > p.max_accel || (has1 && fabs(sddB) > p.max_accel)) viol |= FISS_FLAG_ACCEL;  // :155
+          bool okA, okB;
+          double pxA, pyA, txA, tyA, pxB, pyB, txB, tyB;
+          spline_frame2(sp, a.K, a.Kp, a.search_iters, sA, sB, okA, okB, pxA, pyA, txA, tyA, pxB, pyB, txB, tyB);
+          const double rA = rsqrt(txA * txA + tyA * tyA), rB = rsqrt(txB * txB + tyB * tyB);
+          if (okA) {
+            P2[base + m0] = make_double2(pxA, pyA);
+            U2[base + m0] = make_double2(txA * rA, tyA * rA);
           } else {
-            first_bad = min(first_bad, m);
+            first_bad = min(first_bad, m0);
           }
-          SD[base + m] = s_d;
+          SD[base + m0] = sdA;
+          if (has1) {
+            if (okB) {
+              P2[base + m1] = make_double2(pxB, pyB);
+              U2[base + m1] = make_double2(txB * rB, tyB * rB);
+            } else {
+              first_bad = min(first_bad, m1);
+            }
+            SD[base + m1] = sdB;
+          }
         }
         acc = warp_sum(acc);
         viol = warp_or(viol);
         const int n_cart = warp_min(first_bad);  // n' (:112-113)
+        // checked steps i = e*check_res < t_step_max = min(n', final_time_step - now) (:173-176);
+        // none when the collision stage is skipped for the row (:257-259) or cannot run (n' < 2)
+        const int horizon = min(n_cart, t_left);
+        const bool do_coll = a.M > 0 && horizon > 0 && n_cart >= 2 && (p.collide_all || viol == 0);
+        const int E_row = do_coll ? (horizon + res - 1) / res : 0;
         if (lane == 0) {
           lon_cost[j] = acc;
           lon_viol[j] = viol;
           lon_ncart[j] = n_cart;
-          // checked steps i = e*check_res < t_step_max = min(n', final_time_step - now) (:173-176);
-          // none when the collision stage is skipped for the row (:257-259) or cannot run (n' < 2)
-          const int horizon = min(n_cart, t_left);
-          const bool do_coll = a.M > 0 && horizon > 0 && n_cart >= 2 && (p.collide_all || viol == 0);
-          lon_E[j] = do_coll ? (horizon + res - 1) / res : 0;
+          lon_E[j] = E_row;
+        }
+        // this row's frame points into the per-step bounding boxes of stage A' (order-preserving integer keys,
+        // shared-memory atomics: min / max commute, so the boxes do not depend on the order the rows arrive in)
+        __syncwarp();
+        for (int e = lane; e < E_row; e += 32) {
+          const double2 fp = P2[base + e * res];
+          atomicMin(&bbox_key[4 * e + 0], order_key(fp.x));
+          atomicMax(&bbox_key[4 * e + 1], order_key(fp.x));
+          atomicMin(&bbox_key[4 * e + 2], order_key(fp.y));
+          atomicMax(&bbox_key[4 * e + 3], order_key(fp.y));
         }
       } else {
         // lateral quintic, end (d_end, 0, 0)                        polynomial.py:45-62
@@ -297,15 +359,26 @@ __global__ void __launch_bounds__(kGridThreads, kGridMinCtas) fiss_grid_kernel(c
         const double la5 = (6.0 * Dl - 3.0 * Vl * T + 0.5 * Al * T2) * (iT3 * iT2);
         double acc = 0.0, dmax = 0.0;
         const int base = ii * n_pad;
-        for (int m = lane; m < n; m += 32) {
-          const double t = m * p.tick_t;
-          const double t2 = t * t, t3 = t2 * t, t4 = t3 * t, t5 = t4 * t;
-          const double d = d0 + dv0 * t + la2 * t2 + la3 * t3 + la4 * t4 + la5 * t5;
-          const double d_dd = 2.0 * la2 + 6.0 * la3 * t + 12.0 * la4 * t2 + 20.0 * la5 * t3;
-          const double d_ddd = 6.0 * la3 + 24.0 * la4 * t + 60.0 * la5 * t2;
-          acc += p.w_accel * (d_dd * d_dd) + p.w_jerk * (d_ddd * d_ddd) + p.w_offset * (d * d);  // cost_function.py:45-47
-          dmax = fmax(dmax, fabs(d));  // NaN-ignoring: a NaN row has no frame anyway
-          lat[base + m] = d;
+        for (int m0 = lane; m0 < n; m0 += 64) {  // two steps per lane in lockstep, same accumulation order
+          const int m1 = m0 + 32;
+          const bool has1 = m1 < n;
+          const double tA = m0 * p.tick_t, tB = m1 * p.tick_t;
+          const double tA2 = tA * tA, tA3 = tA2 * tA, tA4 = tA3 * tA, tA5 = tA4 * tA;
+          const double tB2 = tB * tB, tB3 = tB2 * tB, tB4 = tB3 * tB, tB5 = tB4 * tB;
+          const double dA = d0 + dv0 * tA + la2 * tA2 + la3 * tA3 + la4 * tA4 + la5 * tA5;
+          const double dB = d0 + dv0 * tB + la2 * tB2 + la3 * tB3 + la4 * tB4 + la5 * tB5;
+          const double ddA = 2.0 * la2 + 6.0 * la3 * tA + 12.0 * la4 * tA2 + 20.0 * la5 * tA3;
+          const double ddB = 2.0 * la2 + 6.0 * la3 * tB + 12.0 * la4 * tB2 + 20.0 * la5 * tB3;
+          const double dddA = 6.0 * la3 + 24.0 * la4 * tA + 60.0 * la5 * tA2;
+          const double dddB = 6.0 * la3 + 24.0 * la4 * tB + 60.0 * la5 * tB2;
+          acc += p.w_accel * (ddA * ddA) + p.w_jerk * (dddA * dddA) + p.w_offset * (dA * dA);  // cost_function.py:45-47
+          dmax = fmax(dmax, fabs(dA));  // NaN-ignoring: a NaN row has no frame anyway
+          lat[base + m0] = dA;
+          if (has1) {
+            acc += p.w_accel * (ddB * ddB) + p.w_jerk * (dddB * dddB) + p.w_offset * (dB * dB);
+            dmax = fmax(dmax, fabs(dB));
+            lat[base + m1] = dB;
+          }
         }
         acc = warp_sum(acc);
 #pragma unroll
@@ -317,38 +390,19 @@ __global__ void __launch_bounds__(kGridThreads, kGridMinCtas) fiss_grid_kernel(c
       }
     }
     __syncthreads();
+    FISS_PHASE(2);
 
     // ---- stage A': proximity masks.  masks[j][e] gets a bit per obstacle whose centre is within
     // (max|d| + r_ego + r_obs) of the frame point of longitudinal row j at checked step e -- a superset of the
-    // obstacles any candidate on that row can touch there.  Three short passes:
-    //   (1) one lane per checked step boxes the frame points of the rows that check that step;
-    //   (2) one lane per (step, obstacle) tests the obstacle against the box (the same squared-distance expression
+    // obstacles any candidate on that row can touch there.  The per-step bounding boxes of the frame points were
+    // accumulated by the row warps of stage A; here
+    //   (1) one lane per (step, obstacle) tests the obstacle against the box (the same squared-distance expression
     //       as the per-row test, so the box can only over-accept); the few survivors go to a compact list;
-    //   (3) one lane per (survivor, row) runs the per-row test, sets the mask bit and -- the first one to touch a
+    //   (2) one lane per (survivor, row) runs the per-row test, sets the mask bit and -- the first one to touch a
     //       (row, step) -- appends it to the work list of stage B.
     if (a.M > 0) {
       const double dmax = __longlong_as_double((long long)*dmax_bits);
       const double reach0 = (dmax + re) * (1.0 + 1.0e-9) + 1.0e-9;
-      for (int e = threadIdx.x; e < e_pad; e += blockDim.x) {
-        double x0 = CUDART_INF, x1 = -CUDART_INF, y0 = CUDART_INF, y1 = -CUDART_INF;
-        const int m = min(e * res, n_pad - 1);
-        for (int j = 0; j < nv; ++j) {
-          if (e < lon_E[j]) {
-            const double2 fp = P2[j * n_pad + m];
-            x0 = fmin(x0, fp.x);
-            x1 = fmax(x1, fp.x);
-            y0 = fmin(y0, fp.y);
-            y1 = fmax(y1, fp.y);
-          }
-          listed[j * e_pad + e] = 0u;
-          for (int w = 0; w < words; ++w) masks[(j * e_pad + e) * words + w] = 0u;
-        }
-        bbox[4 * e + 0] = x0;  // no row checks this step: the empty box (+inf, -inf) is infinitely far from everything
-        bbox[4 * e + 1] = x1;
-        bbox[4 * e + 2] = y0;
-        bbox[4 * e + 3] = y1;
-      }
-      __syncthreads();
       const uint32_t mp_magic = (1u << 20) / (uint32_t)Mp + 1u;  // q / Mp for q < 2^20 / Mp
       for (int q = threadIdx.x; q < e_pad * Mp; q += blockDim.x) {
         const int e = (int)(((uint32_t)q * mp_magic) >> 20);
@@ -359,12 +413,13 @@ __global__ void __launch_bounds__(kGridThreads, kGridMinCtas) fiss_grid_kernel(c
           const double* slot = obs + row * (4 * Mp) + jo;
           const double ox = slot[0], oy = slot[Mp];
           const double reach = reach0 + oc[2 * Mp + jo] * (1.0 + 1.0e-9);
-          const double bx = fmax(fmax(bbox[4 * e] - ox, ox - bbox[4 * e + 1]), 0.0);
-          const double by = fmax(fmax(bbox[4 * e + 2] - oy, oy - bbox[4 * e + 3]), 0.0);
+          const double bx = fmax(fmax(order_value(bbox_key[4 * e]) - ox, ox - order_value(bbox_key[4 * e + 1])), 0.0);
+          const double by = fmax(fmax(order_value(bbox_key[4 * e + 2]) - oy, oy - order_value(bbox_key[4 * e + 3])), 0.0);
           if (near2(bx, by) <= reach * reach) near_list[atomicAdd(n_near, 1u)] = ((uint32_t)e << 16) | (uint32_t)jo;
         }
       }
       __syncthreads();
+      FISS_PHASE(4);
       const uint32_t n_cand_pairs = *n_near * (uint32_t)nv;
       for (uint32_t q = threadIdx.x; q < n_cand_pairs; q += blockDim.x) {
         const uint32_t c = q / (uint32_t)nv;
@@ -384,6 +439,7 @@ __global__ void __launch_bounds__(kGridThreads, kGridMinCtas) fiss_grid_kernel(c
       }
     }
     __syncthreads();
+    FISS_PHASE(5);
 
     // ---- stage B, collision (has_collision, frenet_optimal_planner.py:168-195): one lane per
     // (lateral row, listed (row, step) pair); exact predicate on the listed obstacles only
@@ -437,6 +493,10 @@ __global__ void __launch_bounds__(kGridThreads, kGridMinCtas) fiss_grid_kernel(c
       }
     }
 
+#ifdef FISS_PHASE_TIMING
+    __syncthreads();
+    FISS_PHASE(6);
+#endif
     // ---- stage B, materialisation (calc_global_paths, frenet_optimal_planner.py:121-134).
     // Lanes = flattened (longitudinal row j, time step m) elements f = j*n_stride + m of the frame tables, cut into
     // blocks of 31 outputs: the 32nd lane of a block only supplies the heading of the next step (kappa_m needs
@@ -520,6 +580,7 @@ __global__ void __launch_bounds__(kGridThreads, kGridMinCtas) fiss_grid_kernel(c
       }
     }
     __syncthreads();
+    FISS_PHASE(7);
 
     // ---- stage C: one lane per candidate -- cost (cost_function.py:41-50) and the flags word
     {
@@ -540,6 +601,10 @@ __global__ void __launch_bounds__(kGridThreads, kGridMinCtas) fiss_grid_kernel(c
       }
     }
   }
+#ifdef FISS_PHASE_TIMING
+  if (threadIdx.x == 0)
+    for (int k = 0; k < 8; ++k) atomicAdd((unsigned long long*)&g_fiss_phase[k], (unsigned long long)phase_acc[k]);
+#endif
 }
 
 }  // namespace fiss

@@ -102,16 +102,8 @@ __device__ __forceinline__ unsigned warp_or(unsigned v) { return __reduce_or_syn
 // Reference line.  `sp` points at [9][Kp]: knots, ax, bx, cx, dx, ay, by, cy, dy.
 // Returns false when s is outside [knots[0], knots[K-1]) (cubic_spline.py:57-60; s == last knot is an
 // IndexError in the reference, treated as outside: SURVEY A.4).  NaN compares false -> outside.
-__device__ __forceinline__ bool spline_frame(const double* __restrict__ sp, int K, int Kp, int iters, double s,
-                                             double& px, double& py, double& tx, double& ty) {
-  if (!(s >= sp[0] && s < sp[K - 1])) return false;
-  int lo = 0, hi = K - 1;  // knots[lo] <= s < knots[hi]  == bisect_right(knots, s) - 1 (cubic_spline.py:112-116)
-  for (int it = 0; it < iters; ++it) {
-    int mid = (lo + hi) >> 1;
-    bool le = sp[mid] <= s;
-    lo = (le && hi - lo > 1) ? mid : lo;
-    hi = (!le && hi - lo > 1) ? mid : hi;
-  }
+__device__ __forceinline__ void spline_eval(const double* __restrict__ sp, int Kp, int lo, double s, double& px,
+                                            double& py, double& tx, double& ty) {
   const double dx = s - sp[lo];
   const double dx2 = dx * dx;
   const double dx3 = dx2 * dx;
@@ -123,7 +115,43 @@ __device__ __forceinline__ bool spline_frame(const double* __restrict__ sp, int 
   py = cy[0] + by * dx + ccy * dx2 + ddy * dx3;
   tx = bx + 2.0 * ccx * dx + 3.0 * ddx * dx2;                  // cubic_spline.py:86
   ty = by + 2.0 * ccy * dx + 3.0 * ddy * dx2;
+}
+
+__device__ __forceinline__ bool spline_frame(const double* __restrict__ sp, int K, int Kp, int iters, double s,
+                                             double& px, double& py, double& tx, double& ty) {
+  if (!(s >= sp[0] && s < sp[K - 1])) return false;
+  int lo = 0, hi = K - 1;  // knots[lo] <= s < knots[hi]  == bisect_right(knots, s) - 1 (cubic_spline.py:112-116)
+  for (int it = 0; it < iters; ++it) {
+    int mid = (lo + hi) >> 1;
+    bool le = sp[mid] <= s;
+    lo = (le && hi - lo > 1) ? mid : lo;
+    hi = (!le && hi - lo > 1) ? mid : hi;
+  }
+  spline_eval(sp, Kp, lo, s, px, py, tx, ty);
   return true;
+}
+
+// Two independent abscissae searched and evaluated in lockstep (two dependency chains per lane instead of one; the
+// searches are the latency of the row stage).  Same arithmetic as spline_frame; out-of-range / NaN abscissae still walk
+// the (in-bounds) search and are reported through okA / okB.
+__device__ __forceinline__ void spline_frame2(const double* __restrict__ sp, int K, int Kp, int iters, double sA, double sB,
+                                              bool& okA, bool& okB, double& pxA, double& pyA, double& txA, double& tyA,
+                                              double& pxB, double& pyB, double& txB, double& tyB) {
+  const double k0 = sp[0], k1 = sp[K - 1];
+  okA = sA >= k0 && sA < k1;
+  okB = sB >= k0 && sB < k1;
+  int loA = 0, hiA = K - 1, loB = 0, hiB = K - 1;
+  for (int it = 0; it < iters; ++it) {
+    const int midA = (loA + hiA) >> 1, midB = (loB + hiB) >> 1;
+    const bool leA = sp[midA] <= sA, leB = sp[midB] <= sB;
+    const bool openA = hiA - loA > 1, openB = hiB - loB > 1;
+    loA = (leA && openA) ? midA : loA;
+    hiA = (!leA && openA) ? midA : hiA;
+    loB = (leB && openB) ? midB : loB;
+    hiB = (!leB && openB) ? midB : hiB;
+  }
+  spline_eval(sp, Kp, loA, sA, pxA, pyA, txA, tyA);
+  spline_eval(sp, Kp, loB, sB, pxB, pyB, txB, tyB);
 }
 
 // Closed-set SAT of two oriented rectangles in centre/axis form; true = they intersect

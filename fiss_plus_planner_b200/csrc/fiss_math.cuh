@@ -49,12 +49,13 @@ __device__ __forceinline__ double ratio_unit(double mn, double mx) {
 }
 
 // 1 / sqrt(h2) for h2 in the normal range: seed (MUFU.RSQ64H) + the cubic step y(1 + e/2 + 3e^2/8), e = 1 - h2 y^2
-// -- the same refinement the CUDA library's rsqrt() applies, without its special-case branch.
+// -- the refinement the CUDA library's rsqrt() applies, in the library's own operation order (so that the result is
+// the library's for every normal input), without its special-case branch.
 __device__ __forceinline__ double rsqrt_normal(double h2) {
   double y;
   asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(h2));
-  const double e = fma(-(h2 * y), y, 1.0);
-  return fma(y, fma(0.375, e, 0.5) * e, y);
+  const double e = fma(h2, -(y * y), 1.0);
+  return fma(fma(e, 0.375, 0.5), y * e, y);
 }
 
 // atan2 for a finite, non-degenerate vector (max(|x|, |y|) in the normal range); ~3e-16 relative.
