@@ -92,6 +92,23 @@ struct fiss_handle {
   std::vector<double> axes_cache;
   int grid_n_max = 0;
   size_t smem_attr[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  // resident CTAs per SM of kernel `which` at (threads, smem): asked from the runtime once per distinct launch shape
+  // (the query costs microseconds on the latency path of every plan() call)
+  struct OccKey { int threads = -1; size_t smem = 0; int occ = 1; } occ_cache[8];
+  template <typename K>
+  cudaError_t occupancy(int which, K kern, int threads, size_t smem, int* out) {
+    OccKey& c = occ_cache[which];
+    if (c.threads != threads || c.smem != smem) {
+      int occ = 1;
+      cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, threads, smem);
+      if (e != cudaSuccess) return e;
+      c.threads = threads;
+      c.smem = smem;
+      c.occ = std::max(occ, 1);
+    }
+    *out = c.occ;
+    return cudaSuccess;
+  }
 };
 
 namespace {
@@ -145,8 +162,7 @@ int32_t launch_eval(fiss_handle* h, cudaStream_t st, LaunchPlan& lp, int which) 
     h->smem_attr[which] = kSmemLimit;
   }
   int occ = 1;
-  FISS_CUDA(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, lp.threads, lp.smem));
-  occ = std::max(occ, 1);
+  FISS_CUDA(h, h->occupancy(which, kern, lp.threads, lp.smem, &occ));
   const int warps = lp.threads / 32;
   const int64_t need = (lp.a.total + warps - 1) / warps;
   lp.grid = (int)std::max<int64_t>(1, std::min<int64_t>(need, (int64_t)h->sm_count * occ));
@@ -267,8 +283,7 @@ int32_t launch_grid(fiss_handle* h, cudaStream_t st, const fiss::GridArgs& a, si
     h->smem_attr[which] = kSmemLimit;
   }
   int occ = 1;
-  FISS_CUDA(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, threads, smem));
-  occ = std::max(occ, 1);
+  FISS_CUDA(h, h->occupancy(which, kern, threads, smem, &occ));
   const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(a.items, (int64_t)h->sm_count * occ));
   kern<<<grid, threads, smem, st>>>(a);
   h->launches++;
