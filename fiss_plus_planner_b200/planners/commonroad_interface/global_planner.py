@@ -132,7 +132,9 @@ class GlobalPlanner(object):
         yaws = np.arctan2(np.diff(pts[:, 1]), np.diff(pts[:, 0]))
         yaws = np.append(yaws, yaws[-1])
         # lane width at every vertex (:91-94)
-        widths = np.concatenate([np.linalg.norm(l.left_vertices - l.right_vertices, axis=1) for l in plan.lanelets])[keep]
+        # (per-vertex 2-norms one at a time, like the reference: the vectorised axis=1 norm rounds differently by 1 ulp)
+        widths = np.concatenate([np.array([np.linalg.norm(l.left_vertices[i] - l.right_vertices[i])
+                                           for i in range(len(l.left_vertices))]) for l in plan.lanelets])[keep]
         plan.concat_centerline = np.column_stack((pts, yaws, widths))
         if view_route:
             print("Global Planning Results:")

@@ -33,6 +33,8 @@ from fiss_plus_planner_b200.planners.commonroad_interface import commonroad_lite
 from fiss_plus_planner_b200.planners.commonroad_interface.vehicle_parameters import VehicleParameterMapping  # noqa: E402
 
 SCENARIOS = ("DEU_Flensburg-1_1_T-1", "DEU_Flensburg-26_1_T-1")   # config #1; a scene where collisions decide
+# the other three demo scenarios with the two cheap searches only (the reference's FOP costs ~1 s per cycle, 80-100 cycles)
+SCENARIOS_SEARCH_ONLY = ("DEU_Lohmar-15_1_T-1", "DEU_Lohmar-54_1_T-1", "DEU_Lohmar-65_1_T-1")
 NUM_SAMPLES = (5, 5, 5)
 
 
@@ -104,11 +106,16 @@ def run(method, scenario, problem, vehicle_params, SCENARIO):
 
 
 def main():
+    only = sys.argv[1:]
     for name in SCENARIOS:
-        one_scenario(name)
+        if not only or name in only:
+            one_scenario(name)
+    for name in SCENARIOS_SEARCH_ONLY:
+        if not only or name in only:
+            one_scenario(name, ("FISS", "FISS+"))
 
 
-def one_scenario(SCENARIO):
+def one_scenario(SCENARIO, methods=("FOP", "FOP+", "FISS", "FISS+")):
     src = os.path.join(rh.REFERENCE_ROOT, "data", "demo", SCENARIO + ".xml")
     scenario, pps = crl.CommonRoadFileReader(src).open()
     problem = list(pps.planning_problem_dict.values())[0]
@@ -127,7 +134,7 @@ def one_scenario(SCENARIO):
     os.remove(tmp)
     rh.attach_shapely_shapes(scenario)
     vehicle_params = VehicleParameterMapping["VW_VANAGON"].value
-    for method in ("FOP", "FOP+", "FISS", "FISS+"):
+    for method in methods:
         run(method, scenario, problem, vehicle_params, SCENARIO)
 
 
