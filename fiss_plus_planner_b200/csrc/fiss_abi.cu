@@ -317,6 +317,11 @@ int32_t eval_grid(fiss_handle* h, cudaStream_t st, const double* d_ego, int B, c
   a.n_pad = (n_max + 2) & ~1;
   a.e_pad = (n_max + p->check_res - 1) / p->check_res;
   a.cost = d_cost; a.flags = d_flags; a.mat = d_mat; a.n_stride = n_stride;
+  a.mat_pitch = a.total * n_stride;
+  a.kap_limit = p->check_curvature ? p->max_curvature : HUGE_VAL;
+  // the lanes address a problem's candidates with 32-bit element offsets
+  if ((int64_t)a.C * n_stride >= (int64_t)1 << 31)
+    return fail(h, FISS_ERR_CAPACITY, "lattice size x n_stride must stay below 2^31 elements");
   // work items: (ego state, horizon[, chunk of lateral rows]).  With few ego states the lateral axis is
   // split so that the launch still covers the SMs (the longitudinal rows are recomputed per chunk).
   const int64_t base_items = (int64_t)B * g->nt;
@@ -325,6 +330,11 @@ int32_t eval_grid(fiss_handle* h, cudaStream_t st, const double* d_ego, int B, c
   a.d_chunk = std::max(1, g->nd / chunks);
   a.n_chunks = (g->nd + a.d_chunk - 1) / a.d_chunk;
   a.items = base_items * a.n_chunks;
+  const auto magic = [](int d) { return (1u << 20) / (uint32_t)std::max(d, 1) + 1u; };
+  a.nv_magic = magic(a.nv);
+  a.mp_magic = magic(a.Mp);
+  a.ns_magic = magic(n_stride);
+  a.ng_magic = magic((a.d_chunk + fiss::kMatRows - 1) / fiss::kMatRows);
   const int warps = std::max(1, std::min(fiss::kGridWarps, std::max(g->nv + a.d_chunk, a.d_chunk * g->nv)));
   // obstacle rows of the checked steps go to shared memory while the CTA stays under the budget
   const int horizon = std::max(0, std::min(n_max, h->final_time_step - p->time_step_now));
@@ -633,16 +643,29 @@ int32_t fiss_pick_winners_dev(fiss_handle* h, void* stream, const double* d_ego,
   if (rc != FISS_OK) return rc;
   FISS_CUDA(h, cudaSetDevice(h->device));
   cudaStream_t st = (cudaStream_t)stream;
-  fiss::fiss_pick_kernel<<<B, fiss::kPickThreads, 0, st>>>(d_cost, d_flags, C, d_best_idx, d_best_cost, d_end, d_best_meta);
-  h->launches++;
-  FISS_CUDA(h, cudaGetLastError());
-  if (d_records) {
+  if (!d_records) {
+    fiss::fiss_pick_kernel<<<B, fiss::kPickThreads, 0, st>>>(d_cost, d_flags, C, d_best_idx, d_best_cost, d_end, d_best_meta);
+    h->launches++;
+    FISS_CUDA(h, cudaGetLastError());
+  } else {  // one launch: the record kernel's warp of problem b picks b's winner first
     LaunchPlan lp{};
     rc = plan_launch(h, p, B, n_stride, lp);
     if (rc != FISS_OK) return rc;
     lp.a.ego = d_ego;
     lp.a.end = d_end;
-    lp.a.sel = d_best_idx;
+    // the winners' flags are already in d_flags: the record launch skips the collision stage and its obstacle rows
+    lp.a.M = 0;
+    if (lp.a.obs_in_smem) {
+      lp.smem -= (size_t)lp.a.E_max * lp.a.Mp * 32;
+      lp.a.obs_in_smem = 0;
+    }
+    lp.a.E_max = 0;
+    lp.a.sel = nullptr;
+    lp.a.pick_cost = d_cost;
+    lp.a.pick_flags = d_flags;
+    lp.a.pick_idx = d_best_idx;
+    lp.a.pick_best = d_best_cost;
+    lp.a.pick_meta = d_best_meta;
     lp.a.B = B;
     lp.a.C = C;
     lp.a.per_problem = 1;

@@ -57,6 +57,10 @@ constexpr int kAxisMax = 64;  // lattice points per axis
 #ifndef FISS_MAT_GROUP
 #define FISS_MAT_GROUP 3
 #endif
+#ifndef FISS_MAT_ILP
+#define FISS_MAT_ILP 3
+#endif
+constexpr int kMatIlp = FISS_MAT_ILP;  // lateral rows whose heading chains advance in lockstep in one lane
 constexpr int kMatRows = FISS_MAT_GROUP;  // lateral rows one materialisation task walks with the same frame points
 
 struct GridArgs {
@@ -83,11 +87,15 @@ struct GridArgs {
   uint32_t* flags;     // [B*C]
   double* mat;         // [5][B*C][n_stride] or NULL
   int32_t n_stride;
+  int64_t mat_pitch;   // elements between two fields of the materialisation = B*C*n_stride
+  // x / d == (x * magic(d)) >> 20 for x * d < 2^20 (host-computed: an integer division costs ~20 issue slots per warp)
+  uint32_t nv_magic, mp_magic, ns_magic, ng_magic;  // d = nv, Mp, n_stride, groups of a full chunk
+  double kap_limit;    // max_curvature when the optional curvature mask is on, +inf otherwise
 };
 
 // Shared-memory carve-up (byte offsets, 16-byte aligned), used by the host for the launch size too.
 struct GridLayout {
-  uint32_t spline, oc, obs, bbox, axes, lon, lat, lon_cost, lat_cost, dmax, lon_viol, lon_ncart, lon_E, npairs, pairs, cflags, masks,
+  uint32_t spline, oc, obs, bbox, bbox_d, axes, lon, lat, lon_cost, lat_cost, dmax, lon_viol, lon_ncart, lon_E, npairs, pairs, cflags, masks,
       listed, near_list, bytes;
 };
 
@@ -101,6 +109,7 @@ __host__ __device__ inline GridLayout grid_layout(int Kp, int Mp, int E_stage, i
   L.oc = o;         o += 4u * Mp * 8u;
   L.obs = o;        o += (uint32_t)E_stage * 4u * Mp * 8u;
   L.bbox = o;       o += (uint32_t)e_pad * 4u * 8u;
+  L.bbox_d = o;     o += (uint32_t)e_pad * 4u * 8u;
   L.axes = o;       o += 4u * kAxisMax * 8u;
   L.lon = o;        o += 5u * nv * n_pad * 8u;
   L.lat = o;        o += (uint32_t)d_chunk * n_pad * 8u;
@@ -145,6 +154,75 @@ __device__ __forceinline__ void grid_pos(const double2* __restrict__ P2, const d
   y = P.y + d * U.x;
 }
 
+// Materialisation of R lateral rows at one (longitudinal row, step) lane: position from the frame points, heading,
+// 1/ds and curvature (calc_global_paths, frenet_optimal_planner.py:121-134), five stores.  The R rows are independent
+// instruction chains in ONE basic block (no vote or branch between them), which is what lets the scheduler overlap
+// their fixed FP64 latencies: a warp's issue rate, not its instruction count, bounds this stage.
+struct MatOut {
+  double* f_x;       // x field of the item's first candidate (NULL: nothing is written)
+  int64_t pitch;     // elements between two fields
+  double kap_limit;  // optional curvature mask (+inf: off)
+  bool has_seg, at_seg, has_kap, writes;
+};
+
+template <int R>
+__device__ __forceinline__ void mat_rows(const MatOut& mo, const double2 Pa, const double2 Ua, const double2 Pb,
+                                         const double2 Ub, double sd_v, const double* __restrict__ Dr, int n_pad, int off,
+                                         int lat_pitch, uint32_t* cf, int nv) {
+  double dx[R], dy[R], yaw[R], inv_ds[R], kap[R];
+  bool ok[R];
+#pragma unroll
+  for (int r = 0; r < R; ++r) {
+    const double da = Dr[r * n_pad], db = Dr[r * n_pad + 1];
+    const double xa = Pa.x - da * Ua.y, ya = Pa.y + da * Ua.x;
+    const double xb = Pb.x - db * Ub.y, yb = Pb.y + db * Ub.x;
+    dx[r] = xb - xa;
+    dy[r] = yb - ya;
+    if (mo.writes) {  // position and speed leave first: their registers are free for the heading chains
+      double* o = mo.f_x + (off + r * lat_pitch);
+      o[0] = mo.at_seg ? xa : xb;
+      o[mo.pitch] = mo.at_seg ? ya : yb;
+      o[3 * mo.pitch] = sd_v;
+    }
+  }
+#ifdef FISS_EXP_NOMATH
+#pragma unroll
+  for (int r = 0; r < R; ++r) { yaw[r] = dx[r]; inv_ds[r] = dy[r]; ok[r] = true; }
+#else
+  segment_fast_n<R>(dx, dy, yaw, inv_ds, ok);
+#endif
+  // a zero-length / non-finite segment takes the library (its special cases are the reference's)
+  bool any_odd = false;
+#pragma unroll
+  for (int r = 0; r < R; ++r) any_odd |= !ok[r] && mo.has_seg;
+  // the next step of the same row is the next lane; the last step of a row never looks at its neighbour
+  // (m >= n' - 1), and lane 31 writes nothing.  c = dyaw / ds with ds = hypot(dx, dy) (:128,132; no unwrap; the
+  // last element is 0/ds)
+  if (__any_sync(kFull, any_odd)) {  // rare, warp-uniform
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      const bool odd = !ok[r] && mo.has_seg;
+      if (odd) yaw[r] = atan2_library(dy[r], dx[r]);
+      const double yaw_next = __shfl_down_sync(kFull, yaw[r], 1);
+      kap[r] = (yaw_next - yaw[r]) * inv_ds[r];
+      if (odd) kap[r] = div_hypot_library(yaw_next - yaw[r], dx[r], dy[r]);
+    }
+  } else {
+#pragma unroll
+    for (int r = 0; r < R; ++r) kap[r] = (__shfl_down_sync(kFull, yaw[r], 1) - yaw[r]) * inv_ds[r];
+  }
+#pragma unroll
+  for (int r = 0; r < R; ++r) {
+    kap[r] = mo.has_kap ? kap[r] : CUDART_NAN;
+    if (fabs(kap[r]) > mo.kap_limit) atomicOr(cf + r * nv, FISS_FLAG_CURVATURE);
+    if (mo.writes) {
+      double* o = mo.f_x + (off + r * lat_pitch);
+      o[2 * mo.pitch] = yaw[r];
+      o[4 * mo.pitch] = kap[r];
+    }
+  }
+}
+
 // kYaw: heading / curvature are needed (materialisation and/or the optional curvature mask).
 template <bool kYaw>
 __global__ void __launch_bounds__(kGridThreads, kGridMinCtas) fiss_grid_kernel(const GridArgs a) {
@@ -176,6 +254,8 @@ __global__ void __launch_bounds__(kGridThreads, kGridMinCtas) fiss_grid_kernel(c
   uint32_t* listed = reinterpret_cast<uint32_t*>(smem_raw + L.listed);        // (row, step) already on the work list
   uint32_t* near_list = reinterpret_cast<uint32_t*>(smem_raw + L.near_list);  // (step << 16 | obstacle) that passed the box
   uint32_t* n_near = npairs + 1;
+  uint32_t* rows_done = npairs + 2;  // longitudinal rows of the item that have folded their frame points into the boxes
+  double* bbox = reinterpret_cast<double*>(smem_raw + L.bbox_d);  // [e_pad][4]: the boxes as doubles (decoded keys)
 
   const fiss_params& p = a.p;
   const int warp = threadIdx.x >> 5;
@@ -225,14 +305,30 @@ __global__ void __launch_bounds__(kGridThreads, kGridMinCtas) fiss_grid_kernel(c
   const double re = sqrt(hle * hle + hwe * hwe);
 
   const int nv = a.nv;
-  const uint32_t nv_magic = (1u << 20) / (uint32_t)nv + 1u;  // c / nv == (c * magic) >> 20 for c < 2^20 / nv
+  const uint32_t nv_magic = a.nv_magic;  // c / nv == (c * magic) >> 20 for c < 2^20 / nv
   const int e_pad = a.e_pad;
   const int words = a.words;
   const int res = p.check_res;
   const int t_left = a.final_time_step - p.time_step_now;
   const uint32_t n_items = (uint32_t)a.items;
   const uint32_t n_chunks = (uint32_t)a.n_chunks, nt = (uint32_t)a.nt;
-  const int64_t row_pitch = a.total * a.n_stride;  // distance between two materialised rows
+
+  // Per-item state of stage A' / B: empty boxes (+inf, -inf: infinitely far from everything), clear masks, list marks
+  // and counters.  Runs before the first item and inside stage C of every item (which is the only reader of cflags and
+  // clears them itself), so that an item costs one barrier less.
+  auto reset_item_state = [&]() {
+    if (threadIdx.x == 0) {
+      *dmax_bits = 0ull;
+      *npairs = 0u;
+      *n_near = 0u;
+      *rows_done = 0u;
+    }
+    for (int q = threadIdx.x; q < 4 * e_pad; q += blockDim.x) bbox_key[q] = order_key((q & 1) ? -CUDART_INF : CUDART_INF);
+    for (int q = threadIdx.x; q < nv * e_pad; q += blockDim.x) listed[q] = 0u;
+    for (int q = threadIdx.x; q < nv * e_pad * words; q += blockDim.x) masks[q] = 0u;
+  };
+  reset_item_state();
+  for (int q = threadIdx.x; q < a.d_chunk * nv; q += blockDim.x) cflags[q] = 0u;
 
   for (uint32_t item = blockIdx.x; item < n_items; item += gridDim.x) {
     const uint32_t bk = item / n_chunks;
@@ -243,23 +339,14 @@ __global__ void __launch_bounds__(kGridThreads, kGridMinCtas) fiss_grid_kernel(c
     const int rows_i = min(a.d_chunk, a.nd - i0);
     const int n_cand = rows_i * nv;
 
-    __syncthreads();  // the previous item's readers are done with the tables (and ax[] is visible)
-    if (threadIdx.x == 0) {
-      *dmax_bits = 0ull;
-      *npairs = 0u;
-      *n_near = 0u;
-    }
-    for (int q = threadIdx.x; q < n_cand; q += blockDim.x) cflags[q] = 0u;
-    // stage A' state: empty boxes (+inf, -inf: infinitely far from everything), clear masks and list marks
-    for (int q = threadIdx.x; q < 4 * e_pad; q += blockDim.x) bbox_key[q] = order_key((q & 1) ? -CUDART_INF : CUDART_INF);
-    for (int q = threadIdx.x; q < nv * e_pad; q += blockDim.x) listed[q] = 0u;
-    for (int q = threadIdx.x; q < nv * e_pad * words; q += blockDim.x) masks[q] = 0u;
+    // the per-item state was reset before the loop / by the previous item's stage C; this barrier also means the
+    // previous item's readers are done with the tables
+    __syncthreads();
     const double T = ax[2 * kAxisMax + k];
     const int n = (int)ax[3 * kAxisMax + k];
     const double* ego = a.ego + 6 * (int64_t)b;
     const double s0 = ego[0], v0 = ego[1], a0 = ego[2], d0 = ego[3], dv0 = ego[4], da0 = ego[5];
     const double T2 = T * T, T3 = T2 * T;
-    __syncthreads();
     FISS_PHASE(1);
 
     // ---- stage A: one warp per row
@@ -334,6 +421,10 @@ __global__ void __launch_bounds__(kGridThreads, kGridMinCtas) fiss_grid_kernel(c
           lon_ncart[j] = n_cart;
           lon_E[j] = E_row;
         }
+        // frame points from the truncation on (and the pad) are NaN: the materialisation reads them without a test and
+        // x, y, heading and curvature of the steps outside the Cartesian part come out NaN by propagation
+        if (kYaw)
+          for (int m = n_cart + lane; m < n_pad; m += 32) P2[base + m] = make_double2(CUDART_NAN, CUDART_NAN);
         // this row's frame points into the per-step bounding boxes of stage A' (order-preserving integer keys,
         // shared-memory atomics: min / max commute, so the boxes do not depend on the order the rows arrive in)
         __syncwarp();
@@ -343,6 +434,17 @@ __global__ void __launch_bounds__(kGridThreads, kGridMinCtas) fiss_grid_kernel(c
           atomicMax(&bbox_key[4 * e + 1], order_key(fp.x));
           atomicMin(&bbox_key[4 * e + 2], order_key(fp.y));
           atomicMax(&bbox_key[4 * e + 3], order_key(fp.y));
+        }
+        // the last row to arrive turns the keys back into doubles, once, for the box test of stage A'
+        __syncwarp();
+        unsigned arrived = 0;
+        if (lane == 0) {
+          __threadfence_block();
+          arrived = atomicAdd(rows_done, 1u);
+        }
+        if (__shfl_sync(kFull, arrived, 0) == (unsigned)nv - 1u) {
+          __threadfence_block();
+          for (int q = lane; q < 4 * e_pad; q += 32) bbox[q] = order_value(bbox_key[q]);
         }
       } else {
         // lateral quintic, end (d_end, 0, 0)                        polynomial.py:45-62
@@ -403,7 +505,7 @@ __global__ void __launch_bounds__(kGridThreads, kGridMinCtas) fiss_grid_kernel(c
     if (a.M > 0) {
       const double dmax = __longlong_as_double((long long)*dmax_bits);
       const double reach0 = (dmax + re) * (1.0 + 1.0e-9) + 1.0e-9;
-      const uint32_t mp_magic = (1u << 20) / (uint32_t)Mp + 1u;  // q / Mp for q < 2^20 / Mp
+      const uint32_t mp_magic = a.mp_magic;  // q / Mp for q < 2^20 / Mp
       for (int q = threadIdx.x; q < e_pad * Mp; q += blockDim.x) {
         const int e = (int)(((uint32_t)q * mp_magic) >> 20);
         const int jo = q - e * Mp;
@@ -413,8 +515,10 @@ __global__ void __launch_bounds__(kGridThreads, kGridMinCtas) fiss_grid_kernel(c
           const double* slot = obs + row * (4 * Mp) + jo;
           const double ox = slot[0], oy = slot[Mp];
           const double reach = reach0 + oc[2 * Mp + jo] * (1.0 + 1.0e-9);
-          const double bx = fmax(fmax(order_value(bbox_key[4 * e]) - ox, ox - order_value(bbox_key[4 * e + 1])), 0.0);
-          const double by = fmax(fmax(order_value(bbox_key[4 * e + 2]) - oy, oy - order_value(bbox_key[4 * e + 3])), 0.0);
+          const double2 box_x = *reinterpret_cast<const double2*>(bbox + 4 * e);
+          const double2 box_y = *reinterpret_cast<const double2*>(bbox + 4 * e + 2);
+          const double bx = fmax(fmax(box_x.x - ox, ox - box_x.y), 0.0);
+          const double by = fmax(fmax(box_y.x - oy, oy - box_y.y), 0.0);
           if (near2(bx, by) <= reach * reach) near_list[atomicAdd(n_near, 1u)] = ((uint32_t)e << 16) | (uint32_t)jo;
         }
       }
@@ -507,75 +611,67 @@ __global__ void __launch_bounds__(kGridThreads, kGridMinCtas) fiss_grid_kernel(c
     // is what hides the FP64 latency at 2-3 resident CTAs per SM.
     if (kYaw) {
       const int ns = a.n_stride;
-      const uint32_t ns_magic = (1u << 20) / (uint32_t)ns + 1u;  // f / ns for f < 2^20 / ns
+      const uint32_t ns_magic = a.ns_magic;  // f / ns for f < 2^20 / ns
       const int n_blocks = (nv * ns + 30) / 31;
-      const uint32_t nb_magic = (1u << 20) / (uint32_t)n_blocks + 1u;
       const int n_groups = (rows_i + kMatRows - 1) / kMatRows;
-      // element offset of candidate (i0, j = 0, k) in a materialised row
-      double* const mat_item = a.mat ? a.mat + ((int64_t)b * a.C + (int64_t)i0 * a.sd + (int64_t)k * a.st) * ns : nullptr;
-      const int64_t lat_pitch = (int64_t)a.sd * ns;
+      const uint32_t ng_magic = rows_i == a.d_chunk ? a.ng_magic : (1u << 20) / (uint32_t)n_groups + 1u;
+      MatOut mo;
+      // the x field of candidate (i0, j = 0, k): uniform per item; the lanes add 32-bit element offsets
+      // (one candidate set's field is C * n_stride < 2^31 elements, checked by the host)
+      mo.f_x = a.mat ? a.mat + ((int64_t)b * a.C + (int64_t)i0 * a.sd + (int64_t)k * a.st) * ns : nullptr;
+      mo.pitch = a.mat_pitch;
+      mo.kap_limit = a.kap_limit;
+      const int lat_pitch = a.sd * ns;
       const int lon_pitch = a.sv * ns;
-      for (int task = warp; task < n_groups * n_blocks; task += wpc) {
-        const int grp = (int)(((uint32_t)task * nb_magic) >> 20);
-        const int f = (task - grp * n_blocks) * 31 + lane;
-        const int j = min((int)(((uint32_t)f * ns_magic) >> 20), nv - 1);
-        const int m = f - j * ns;  // >= ns for the lanes past the end of the table
-        const int tb = j * n_pad;
-        const int n_cart = lon_ncart[j];
-        const bool in_cart = m < n_cart;                 // (n' <= n <= ns)
-        const bool has_seg = in_cart && n_cart >= 2;
-        const bool lone = in_cart && n_cart < 2;         // n' == 1: the single point; yaw / ds / c stay empty (:121)
-        // yaw_m = atan2 of segment min(m, n'-2): the last point repeats the previous heading (:127-130)
-        const int seg = has_seg ? min(m, n_cart - 2) : 0;
-        // Lanes outside the Cartesian part carry NaN frame points: x, y, heading and curvature come out NaN by
-        // propagation, so the per-row code below is straight-line for every lane.
-        const double2 nan2 = make_double2(CUDART_NAN, CUDART_NAN);
-        const double2 Pa = in_cart ? P2[tb + seg] : nan2;
-        const double2 Ua = U2[tb + seg];
-        const double2 Pb = in_cart ? P2[tb + seg + 1] : nan2;
-        const double2 Ub = U2[tb + seg + 1];
-        const bool at_seg = m == seg;
-        const bool has_kap = m < n_cart - 1;
-        const bool writes = mat_item != nullptr && lane < 31 && m < ns;
-        const double sd_v = m < n ? SD[tb + min(m, n_pad - 1)] : CUDART_NAN;
+      // tasks t = blk * n_groups + grp, dealt to the warps as contiguous ranges: consecutive tasks of a warp mostly
+      // share their block, whose lane set-up (indices, predicates) is redone only when the block changes
+      const int n_tasks = n_groups * n_blocks;
+      const int t_begin = (warp * n_tasks) / wpc, t_end = ((warp + 1) * n_tasks) / wpc;
+      int blk = (int)(((uint32_t)t_begin * ng_magic) >> 20);
+      int grp = t_begin - blk * n_groups;
+      bool fresh = true;
+      const double2* fp = P2;  // &P2[row j][segment]
+      int j = 0, seg = 0, off_jm = 0;
+      double sd_v = 0.0;
+      for (int t = t_begin; t < t_end; ++t) {
+        if (fresh) {
+          const int f = blk * 31 + lane;
+          j = min((int)(((uint32_t)f * ns_magic) >> 20), nv - 1);
+          const int m = f - j * ns;  // >= ns for the lanes past the end of the table
+          const int n_cart = lon_ncart[j];
+          const bool in_cart = m < n_cart;  // (n' <= n <= ns)
+          // yaw_m = atan2 of segment min(m, n'-2): the last point repeats the previous heading (:127-130).  Steps
+          // outside the Cartesian part read NaN frame points (stage A), and so does the neighbour of a lone point
+          // (n' == 1: yaw / ds / c stay empty, :121).
+          seg = in_cart ? max(min(m, n_cart - 2), 0) : min(m, n_pad - 2);
+          fp = P2 + j * n_pad + seg;
+          mo.has_seg = in_cart && n_cart >= 2;
+          mo.at_seg = m == seg;
+          mo.has_kap = m < n_cart - 1 && lane < 31;  // lane 31 only supplies the next heading
+          mo.writes = mo.f_x != nullptr && lane < 31 && m < ns;
+#ifdef FISS_EXP_NOSTORE
+          mo.writes = mo.writes && a.B < 0;
+#endif
+          sd_v = m < n ? SD[j * n_pad + min(m, n_pad - 1)] : CUDART_NAN;
+          off_jm = j * lon_pitch + m;
+        }
+        const double2 Pa = fp[0], Pb = fp[1];
+        const double2 Ua = fp[row_len], Ub = fp[row_len + 1];  // U2 = P2 + row_len
         const int i_first = grp * kMatRows;
         const double* Dr = lat + i_first * n_pad + seg;
-        double* o = mat_item + ((int64_t)i_first * lat_pitch + (j * lon_pitch + m));
-#pragma unroll
-        for (int r = 0; r < kMatRows; ++r) {
-          if (i_first + r < rows_i) {  // warp-uniform
-            const double da = Dr[0], db = Dr[1];
-            const double xa = Pa.x - da * Ua.y, ya = Pa.y + da * Ua.x;
-            const double xb = Pb.x - db * Ub.y, yb = Pb.y + db * Ub.x;
-            const double dx = xb - xa, dy = yb - ya;
-            double yaw, inv_ds;
-            // a zero-length / non-finite segment takes the library (its special cases are the reference's)
-            const bool odd = !segment_fast(dx, dy, yaw, inv_ds) && has_seg;
-            if (__any_sync(kFull, odd || lone)) {  // rare, warp-uniform
-              if (odd) yaw = atan2_library(dy, dx);
-              if (lone) yaw = CUDART_NAN;
-            }
-            // the next step of the same row is the next lane; the last step of a row never looks at its
-            // neighbour (m >= n' - 1), and lane 31 writes nothing
-            const double yaw_next = __shfl_down_sync(kFull, yaw, 1);
-            // c = dyaw / ds with ds = hypot(dx, dy) (:128,132; no unwrap; the last element is 0/ds)
-            double kap = (yaw_next - yaw) * inv_ds;
-            if (__any_sync(kFull, odd)) {
-              if (odd) kap = div_hypot_library(yaw_next - yaw, dx, dy);
-            }
-            kap = has_kap ? kap : CUDART_NAN;
-            if (p.check_curvature && has_kap && lane < 31 && fabs(kap) > p.max_curvature)
-              atomicOr(&cflags[(i_first + r) * nv + j], FISS_FLAG_CURVATURE);
-            if (writes) {
-              o[0] = at_seg ? xa : xb;
-              o[row_pitch] = at_seg ? ya : yb;
-              o[2 * row_pitch] = yaw;
-              o[3 * row_pitch] = sd_v;
-              o[4 * row_pitch] = kap;
-            }
-            o += lat_pitch;
-            Dr += n_pad;
-          }
+        const int off = i_first * lat_pitch + off_jm;
+        uint32_t* cf = cflags + i_first * nv + j;
+        const int rows_here = min(kMatRows, rows_i - i_first);  // warp-uniform
+        int r = 0;
+        for (; r + kMatIlp <= rows_here; r += kMatIlp)
+          mat_rows<kMatIlp>(mo, Pa, Ua, Pb, Ub, sd_v, Dr + r * n_pad, n_pad, off + r * lat_pitch, lat_pitch, cf + r * nv, nv);
+        for (; r < rows_here; ++r)
+          mat_rows<1>(mo, Pa, Ua, Pb, Ub, sd_v, Dr + r * n_pad, n_pad, off + r * lat_pitch, lat_pitch, cf + r * nv, nv);
+        fresh = false;
+        if (++grp == n_groups) {
+          grp = 0;
+          ++blk;
+          fresh = true;
         }
       }
     }
@@ -593,12 +689,14 @@ __global__ void __launch_bounds__(kGridThreads, kGridMinCtas) fiss_grid_kernel(c
         const int n_cart = lon_ncart[j];
         const unsigned viol = lon_viol[j];
         unsigned extra = cflags[cidx];
+        cflags[cidx] = 0u;
         // n' == 1 with obstacles: traj.yaw[0] raises inside the try => "collision" (:178-182)
         if (a.M > 0 && min(n_cart, t_left) > 0 && n_cart < 2 && (p.collide_all || viol == 0)) extra |= FISS_FLAG_COLLISION;
         const int64_t out_id = id_base + ii * a.sd + j * a.sv;
         a.cost[out_id] = (cost_time + (lon_cost[j] + lat_cost[ii])) * inv_n;
         a.flags[out_id] = viol | extra | ((uint32_t)n_cart << FISS_FLAG_NCART_SHIFT);
       }
+      reset_item_state();
     }
   }
 #ifdef FISS_PHASE_TIMING

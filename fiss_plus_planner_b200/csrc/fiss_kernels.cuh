@@ -58,6 +58,13 @@ struct EvalArgs {
   int32_t n_stride;
   int32_t n_pad;    // per-warp scratch row length (>= max n, multiple of 2)
   int32_t e_cap;    // per-warp capacity of the compact checked-step arrays (>= ceil(max n / check_res))
+  // full-record mode with the pick fused in (one launch instead of pick + records): the warp of record r first
+  // takes the argmin over problem r's C candidates of pick_cost / pick_flags, publishes it, then writes its record
+  const double* pick_cost;     // [total][C] or NULL (then `sel` names the candidates)
+  const uint32_t* pick_flags;  // [total][C]
+  int32_t* pick_idx;           // [total] winner (-1: none)
+  double* pick_best;           // [total] its cost (+inf: none)
+  int32_t* pick_meta;          // [total][2] (n, n') of the winner, or NULL
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -97,6 +104,38 @@ __device__ __forceinline__ double warp_sum(double v) {
 }
 __device__ __forceinline__ int warp_min(int v) { return __reduce_min_sync(kFull, v); }
 __device__ __forceinline__ unsigned warp_or(unsigned v) { return __reduce_or_sync(kFull, v); }
+
+// argmin with the reference's tie rule: among feasible candidates the minimum cost, and among equal minima the
+// LARGEST index (`min_cost >= cost` scan, frenet_optimal_planner.py:263-268).  NaN costs never win (SURVEY 5:
+// NaN/Inf candidates are masked infeasible).  The selection is associative and commutative, so any reduction
+// order gives the reference's winner.
+__device__ __forceinline__ bool better(double c, int i, double bc, int bi) {
+  return (c < bc) || (c == bc && i > bi);
+}
+__device__ __forceinline__ void pick_scan(const double* __restrict__ pc, const uint32_t* __restrict__ pf, int C,
+                                          int first, int stride, double& bc, int& bi) {
+  bc = CUDART_INF;
+  bi = -1;
+  for (int i = first; i < C; i += stride) {
+    const double c = pc[i];
+    const bool feasible = (pf[i] & FISS_FLAG_INFEASIBLE_MASK) == 0 && c <= CUDART_INF;  // NaN -> false
+    if (feasible && (bi < 0 || better(c, i, bc, bi))) {
+      bc = c;
+      bi = i;
+    }
+  }
+}
+__device__ __forceinline__ void pick_warp_reduce(double& bc, int& bi) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const double oc = __shfl_xor_sync(kFull, bc, o);
+    const int oi = __shfl_xor_sync(kFull, bi, o);
+    if (oi >= 0 && (bi < 0 || better(oc, oi, bc, bi))) {
+      bc = oc;
+      bi = oi;
+    }
+  }
+}
 
 // ------------------------------------------------------------------------------------------------
 // Reference line.  `sp` points at [9][Kp]: knots, ax, bx, cx, dx, ay, by, cy, dy.
@@ -472,7 +511,25 @@ __global__ void __launch_bounds__(kThreads) fiss_eval_kernel(const EvalArgs a) {
   for (int64_t id = (int64_t)blockIdx.x * wpc + warp; id < a.total; id += warps_total) {
     int b, c;
     if (kRec) {
-      const int c_sel = a.sel ? a.sel[id] : (int)id;
+      int c_sel;
+      if (a.pick_cost) {  // fused pick: this warp owns problem `id`
+        const double* pc = a.pick_cost + id * (int64_t)a.C;
+        const uint32_t* pf = a.pick_flags + id * (int64_t)a.C;
+        double bc;
+        pick_scan(pc, pf, a.C, lane, 32, bc, c_sel);
+        pick_warp_reduce(bc, c_sel);
+        if (lane == 0) {
+          a.pick_idx[id] = c_sel;
+          a.pick_best[id] = c_sel >= 0 ? bc : CUDART_INF;
+          if (a.pick_meta) {  // (n, n') of the winner, for the host to cut the ragged record rows
+            a.pick_meta[2 * id] = c_sel >= 0 ? (int)a.end[4 * (int64_t)c_sel + 3] : 0;
+            a.pick_meta[2 * id + 1] =
+                c_sel >= 0 ? (int)((pf[c_sel] >> FISS_FLAG_NCART_SHIFT) & FISS_FLAG_NCART_MASK) : 0;
+          }
+        }
+      } else {
+        c_sel = a.sel ? a.sel[id] : (int)id;
+      }
       b = a.per_problem ? (int)id : 0;
       c = c_sel;
       if (c < 0) {  // no winner for this problem: an all-NaN record
@@ -500,15 +557,10 @@ __global__ void __launch_bounds__(kThreads) fiss_eval_kernel(const EvalArgs a) {
 }
 
 // ------------------------------------------------------------------------------------------------
-// argmin per problem with the reference's tie rule: among feasible candidates take the minimum cost,
-// and among equal minima the LARGEST index (`min_cost >= cost` scan, frenet_optimal_planner.py:263-268).
-// One CTA per problem; block-level reduction through shared memory after a warp-shuffle stage.
+// argmin per problem (tie rule: see better()).  One CTA per problem; block-level reduction through shared memory
+// after a warp-shuffle stage.  Used when only the winners are wanted; with records the pick is fused into the record
+// kernel (EvalArgs::pick_cost).
 constexpr int kPickThreads = 128;
-
-__device__ __forceinline__ bool better(double c, int i, double bc, int bi) {
-  // NaN costs never win (NaN/Inf candidates are masked infeasible)
-  return (c < bc) || (c == bc && i > bi);
-}
 
 __global__ void __launch_bounds__(kPickThreads) fiss_pick_kernel(const double* __restrict__ cost,
                                                                  const uint32_t* __restrict__ flags, int C,
@@ -521,25 +573,10 @@ __global__ void __launch_bounds__(kPickThreads) fiss_pick_kernel(const double* _
   const int b = blockIdx.x;
   const double* pc = cost + (int64_t)b * C;
   const uint32_t* pf = flags + (int64_t)b * C;
-  double bc = CUDART_INF;
-  int bi = -1;
-  for (int i = threadIdx.x; i < C; i += kPickThreads) {
-    const double c = pc[i];
-    const bool feasible = (pf[i] & FISS_FLAG_INFEASIBLE_MASK) == 0 && c <= CUDART_INF;  // NaN -> false
-    if (feasible && (bi < 0 || better(c, i, bc, bi))) {
-      bc = c;
-      bi = i;
-    }
-  }
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) {
-    const double oc = __shfl_xor_sync(kFull, bc, o);
-    const int oi = __shfl_xor_sync(kFull, bi, o);
-    if (oi >= 0 && (bi < 0 || better(oc, oi, bc, bi))) {
-      bc = oc;
-      bi = oi;
-    }
-  }
+  double bc;
+  int bi;
+  pick_scan(pc, pf, C, threadIdx.x, kPickThreads, bc, bi);
+  pick_warp_reduce(bc, bi);
   if ((threadIdx.x & 31) == 0) {
     s_cost[threadIdx.x >> 5] = bc;
     s_idx[threadIdx.x >> 5] = bi;

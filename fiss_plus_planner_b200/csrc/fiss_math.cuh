@@ -81,6 +81,82 @@ __device__ __forceinline__ bool segment_fast(double dx, double dy, double& yaw, 
   return ((unsigned)__double2hiint(h2) - 0x10000000u) < 0x60000000u;
 }
 
+// R segments in lockstep: the same arithmetic as segment_fast, written so that the R dependency chains advance together
+// (ratio, polynomial and rsqrt steps interleaved in program order).  A warp's issue rate through these fixed-latency
+// FP64 chains -- 8 cycles per dependent DFMA on sm_100 -- is what bounds the materialisation stage; two chains per
+// lane halve the exposed latency.
+template <int R>
+__device__ __forceinline__ void segment_fast_n(const double (&dx)[R], const double (&dy)[R], double (&yaw)[R],
+                                               double (&inv_ds)[R], bool (&valid)[R]) {
+  double mx[R], mn[R], r[R], e[R], q[R], u[R], w[R], pe[R], po[R], h2[R];
+  bool steep[R], neg[R];
+#pragma unroll
+  for (int i = 0; i < R; ++i) {
+    const double ax = fabs(dx[i]), ay = fabs(dy[i]);
+    steep[i] = ay > ax;
+    neg[i] = dx[i] < 0.0;
+    mx[i] = steep[i] ? ay : ax;
+    mn[i] = steep[i] ? ax : ay;
+    h2[i] = fma(dx[i], dx[i], dy[i] * dy[i]);
+  }
+  // ratio_unit
+#pragma unroll
+  for (int i = 0; i < R; ++i) asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r[i]) : "d"(mx[i]));
+#pragma unroll
+  for (int i = 0; i < R; ++i) e[i] = fma(-mx[i], r[i], 1.0);
+#pragma unroll
+  for (int i = 0; i < R; ++i) e[i] = fma(e[i], e[i], e[i]);
+#pragma unroll
+  for (int i = 0; i < R; ++i) r[i] = fma(r[i], e[i], r[i]);
+#pragma unroll
+  for (int i = 0; i < R; ++i) q[i] = mn[i] * r[i];
+#pragma unroll
+  for (int i = 0; i < R; ++i) e[i] = fma(-mx[i], q[i], mn[i]);
+#pragma unroll
+  for (int i = 0; i < R; ++i) q[i] = fma(r[i], e[i], q[i]);
+  // atan_unit
+#pragma unroll
+  for (int i = 0; i < R; ++i) u[i] = q[i] * q[i];
+#pragma unroll
+  for (int i = 0; i < R; ++i) w[i] = u[i] * u[i];
+#pragma unroll
+  for (int i = 0; i < R; ++i) {
+    pe[i] = kAtanP[18];
+    po[i] = kAtanP[17];
+  }
+#pragma unroll
+  for (int k = 16; k >= 2; k -= 2) {
+#pragma unroll
+    for (int i = 0; i < R; ++i) {
+      pe[i] = fma(pe[i], w[i], kAtanP[k]);
+      po[i] = fma(po[i], w[i], kAtanP[k - 1]);
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < R; ++i) pe[i] = fma(pe[i], w[i], kAtanP[0]);
+#pragma unroll
+  for (int i = 0; i < R; ++i) pe[i] = fma(u[i], po[i], pe[i]);
+#pragma unroll
+  for (int i = 0; i < R; ++i) po[i] = q[i] * u[i];
+#pragma unroll
+  for (int i = 0; i < R; ++i) {
+    const double a = fma(po[i], pe[i], q[i]);
+    const double off = steep[i] ? 1.5707963267948966 : (neg[i] ? 3.141592653589793 : 0.0);
+    const double sa = (steep[i] != neg[i]) ? -a : a;
+    yaw[i] = copysign(off + sa, dy[i]);
+  }
+  // rsqrt_normal
+  double y[R];
+#pragma unroll
+  for (int i = 0; i < R; ++i) asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y[i]) : "d"(h2[i]));
+#pragma unroll
+  for (int i = 0; i < R; ++i) e[i] = fma(h2[i], -(y[i] * y[i]), 1.0);
+#pragma unroll
+  for (int i = 0; i < R; ++i) inv_ds[i] = fma(fma(e[i], 0.375, 0.5), y[i] * e[i], y[i]);
+#pragma unroll
+  for (int i = 0; i < R; ++i) valid[i] = ((unsigned)__double2hiint(h2[i]) - 0x10000000u) < 0x60000000u;
+}
+
 // Out-of-line library calls for the rare lanes (kept out of the hot loop's register budget).
 __device__ __noinline__ double atan2_library(double y, double x) { return atan2(y, x); }
 __device__ __noinline__ double div_hypot_library(double num, double dx, double dy) { return num / hypot(dx, dy); }
