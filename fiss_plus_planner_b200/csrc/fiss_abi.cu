@@ -166,6 +166,21 @@ int32_t launch_eval(fiss_handle* h, cudaStream_t st, LaunchPlan& lp, int which) 
   const int warps = lp.threads / 32;
   const int64_t need = (lp.a.total + warps - 1) / warps;
   lp.grid = (int)std::max<int64_t>(1, std::min<int64_t>(need, (int64_t)h->sm_count * occ));
+  if (lp.a.after_producer) {  // programmatic dependent launch behind the kernel that produces pick_cost / pick_flags
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3((unsigned)lp.grid);
+    cfg.blockDim = dim3((unsigned)lp.threads);
+    cfg.dynamicSmemBytes = lp.smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr{};
+    attr.id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr.val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = &attr;
+    cfg.numAttrs = 1;
+    FISS_CUDA(h, cudaLaunchKernelEx(&cfg, kern, lp.a));
+    h->launches++;
+    return FISS_OK;
+  }
   kern<<<lp.grid, lp.threads, lp.smem, st>>>(lp.a);
   h->launches++;
   FISS_CUDA(h, cudaGetLastError());
@@ -319,9 +334,6 @@ int32_t eval_grid(fiss_handle* h, cudaStream_t st, const double* d_ego, int B, c
   a.cost = d_cost; a.flags = d_flags; a.mat = d_mat; a.n_stride = n_stride;
   a.mat_pitch = a.total * n_stride;
   a.kap_limit = p->check_curvature ? p->max_curvature : HUGE_VAL;
-  // the lanes address a problem's candidates with 32-bit element offsets
-  if ((int64_t)a.C * n_stride >= (int64_t)1 << 31)
-    return fail(h, FISS_ERR_CAPACITY, "lattice size x n_stride must stay below 2^31 elements");
   // work items: (ego state, horizon[, chunk of lateral rows]).  With few ego states the lateral axis is
   // split so that the launch still covers the SMs (the longitudinal rows are recomputed per chunk).
   const int64_t base_items = (int64_t)B * g->nt;
@@ -329,25 +341,44 @@ int32_t eval_grid(fiss_handle* h, cudaStream_t st, const double* d_ego, int B, c
   int chunks = (int)std::min<int64_t>(g->nd, std::max<int64_t>(1, (want + base_items - 1) / base_items));
   a.d_chunk = std::max(1, g->nd / chunks);
   a.n_chunks = (g->nd + a.d_chunk - 1) / a.d_chunk;
-  a.items = base_items * a.n_chunks;
-  const auto magic = [](int d) { return (1u << 20) / (uint32_t)std::max(d, 1) + 1u; };
-  a.nv_magic = magic(a.nv);
-  a.mp_magic = magic(a.Mp);
-  a.ns_magic = magic(n_stride);
-  a.ng_magic = magic((a.d_chunk + fiss::kMatRows - 1) / fiss::kMatRows);
-  const int warps = std::max(1, std::min(fiss::kGridWarps, std::max(g->nv + a.d_chunk, a.d_chunk * g->nv)));
-  // obstacle rows of the checked steps go to shared memory while the CTA stays under the budget
+  // obstacle rows (centres) of the checked steps go to shared memory while the CTA stays under the budget, else
+  // they are read from global memory / L2
   const int horizon = std::max(0, std::min(n_max, h->final_time_step - p->time_step_now));
   const int E_max = h->M > 0 ? (horizon + p->check_res - 1) / p->check_res : 0;
-  // obstacle rows of the checked steps in shared memory while the CTA stays under the budget, else read from L2
+  const auto magic = [](int d) { return (1u << 20) / (uint32_t)std::max(d, 1) + 1u; };
+  a.nv_magic = magic(a.nv);
+  a.ns_magic = magic(n_stride);
+  const int n_groups = (a.d_chunk + fiss::kMatRows - 1) / fiss::kMatRows;
+  a.ng_magic = magic(n_groups);
+  // (ego, horizon) pairs per work item: as many as keep kGridMinCtas CTAs per SM resident and every CTA supplied with
+  // a few items (FISS_GRID_SLOTS overrides the upper bound, for A/B runs)
+  static const bool slots_forced = std::getenv("FISS_GRID_SLOTS") != nullptr;  // also waives the supply rule (tests)
+  static const int slots_cap = slots_forced ? std::max(1, std::min(fiss::kMaxSlots, std::atoi(std::getenv("FISS_GRID_SLOTS")))) : 2;
   fiss::GridLayout L{};
-  a.E_stage = E_max;
-  L = fiss::grid_layout(a.Kp, a.Mp, a.E_stage, a.nv, a.d_chunk, a.n_pad, a.e_pad, a.words);
-  if (L.bytes > kSmemCtaBudget) {
-    a.E_stage = 0;
-    L = fiss::grid_layout(a.Kp, a.Mp, a.E_stage, a.nv, a.d_chunk, a.n_pad, a.e_pad, a.words);
+  for (a.slots = a.n_chunks > 1 ? 1 : slots_cap;; --a.slots) {
+    // the kernel's multiply-shift divisions are exact below 2^20
+    const int64_t lon_elems = (int64_t)a.slots * a.nv * n_stride + 32, n_blocks = (lon_elems + 30) / 31;
+    const bool exact = lon_elems * n_stride < (1 << 20) && (int64_t)a.slots * a.d_chunk * a.nv * a.nv < (1 << 20) &&
+                       n_blocks * n_groups * n_groups < (1 << 20) && (int64_t)a.slots * a.C * n_stride < ((int64_t)1 << 31);
+    a.E_stage = E_max;
+    L = fiss::grid_layout(a.Kp, a.Mp, a.E_stage, a.nv, a.d_chunk, a.n_pad, a.e_pad, a.words, a.slots);
+    const bool supplied = slots_forced || base_items / a.slots >= 2 * (int64_t)fiss::kGridMinCtas * h->sm_count;
+    if (a.slots > 1) {
+      if (exact && supplied && L.bytes <= kSmemCtaBudget) break;
+      continue;
+    }
+    if (!exact) return fail(h, FISS_ERR_CAPACITY, "lattice too large for the kernel's index arithmetic (nv * n_stride^2 must stay below 2^20)");
+    if (L.bytes > kSmemCtaBudget) {
+      a.E_stage = 0;
+      L = fiss::grid_layout(a.Kp, a.Mp, a.E_stage, a.nv, a.d_chunk, a.n_pad, a.e_pad, a.words, a.slots);
+    }
+    break;
   }
+  a.items = ((base_items + a.slots - 1) / a.slots) * a.n_chunks;
+  const int warps = std::max(1, std::min(fiss::kGridWarps, a.slots * std::max(g->nv + a.d_chunk, a.d_chunk * g->nv)));
   if (L.bytes > kSmemLimit) return fail(h, FISS_ERR_CAPACITY, "lattice row tables exceed 227 KB of shared memory");
+  a.lay = L;
+  a.row_len = a.slots * a.nv * a.n_pad;
   const bool yaw = d_mat != nullptr || p->check_curvature;
   return yaw ? launch_grid<true>(h, st, a, L.bytes, warps * 32, 4) : launch_grid<false>(h, st, a, L.bytes, warps * 32, 3);
 }
@@ -666,6 +697,8 @@ int32_t fiss_pick_winners_dev(fiss_handle* h, void* stream, const double* d_ego,
     lp.a.pick_idx = d_best_idx;
     lp.a.pick_best = d_best_cost;
     lp.a.pick_meta = d_best_meta;
+    lp.a.after_producer = 1;  // everything the kernel touches before its dependency wait (spline, obstacle constants)
+                              // was uploaded synchronously by fiss_set_spline / fiss_set_obstacles
     lp.a.B = B;
     lp.a.C = C;
     lp.a.per_problem = 1;

@@ -29,6 +29,9 @@
 // so a candidate costs ~2 table reads per step instead of two polynomial solves, a 7-step segment
 // search and an M x n/2 obstacle sweep.  All arithmetic is FP64 with the same expressions as the
 // generic kernel in fiss_kernels.cuh (masks, n' and winners are bit-identical between the two).
+//
+// A work item carries `slots` consecutive (ego, horizon) pairs ("slots"): their rows share the stages, the barriers,
+// the per-step bounding boxes and the item bookkeeping -- per-item costs that one 54-candidate slot amortises badly.
 #pragma once
 
 #include "fiss_kernels.cuh"
@@ -54,6 +57,7 @@ constexpr int kGridThreads = kGridWarps * 32;
 #endif
 constexpr int kGridMinCtas = FISS_GRID_MIN_CTAS;  // resident CTAs per SM the register budget is capped for
 constexpr int kAxisMax = 64;  // lattice points per axis
+constexpr int kMaxSlots = 4;  // (ego, horizon) pairs per work item
 #ifndef FISS_MAT_GROUP
 #define FISS_MAT_GROUP 3
 #endif
@@ -63,6 +67,12 @@ constexpr int kAxisMax = 64;  // lattice points per axis
 constexpr int kMatIlp = FISS_MAT_ILP;  // lateral rows whose heading chains advance in lockstep in one lane
 constexpr int kMatRows = FISS_MAT_GROUP;  // lateral rows one materialisation task walks with the same frame points
 
+// Shared-memory carve-up (byte offsets, 16-byte aligned), used by the host for the launch size too.
+struct GridLayout {
+  uint32_t spline, oc, obs, bbox, bbox_d, axes, slot_d, slot_base, slot_off, lon, lat, lon_cost, lat_cost, dmax, lon_viol,
+      lon_ncart, lon_E, counters, pairs, cflags, masks, listed, near_list, bytes;
+};
+
 struct GridArgs {
   const double* ego;   // [B][6]
   const double* axes;  // [4][kAxisMax]: d_end, v_end, T, n (step count as a double)
@@ -71,7 +81,8 @@ struct GridArgs {
   int32_t B, C;
   int32_t d_chunk;     // lateral rows per work item
   int32_t n_chunks;
-  int64_t items;       // B * nt * n_chunks
+  int32_t slots;       // (ego, horizon) pairs per work item; > 1 only when the lateral axis is not chunked
+  int64_t items;       // ceil(B * nt / slots) * n_chunks
   int64_t total;       // B * C
   fiss_params p;
   const double* spline;  // [9][Kp]
@@ -79,7 +90,7 @@ struct GridArgs {
   const double* obs_tab;    // [T_obs][4][Mp]
   const double* obs_const;  // [4][Mp]
   int32_t M, Mp, mp_shift, T_obs, final_time_step;
-  int32_t E_stage;     // obstacle rows staged in shared memory (0: read them from global / L2)
+  int32_t E_stage;     // obstacle rows (centres only) staged in shared memory (0: read them from global / L2)
   int32_t words;       // 32-bit mask words per (row, step) = max(1, Mp/32)
   int32_t n_pad;       // table row length (>= max n + 1, even)
   int32_t e_pad;       // mask row length (>= max checked steps)
@@ -89,41 +100,41 @@ struct GridArgs {
   int32_t n_stride;
   int64_t mat_pitch;   // elements between two fields of the materialisation = B*C*n_stride
   // x / d == (x * magic(d)) >> 20 for x * d < 2^20 (host-computed: an integer division costs ~20 issue slots per warp)
-  uint32_t nv_magic, mp_magic, ns_magic, ng_magic;  // d = nv, Mp, n_stride, groups of a full chunk
+  uint32_t nv_magic, ns_magic, ng_magic;  // d = nv, n_stride, groups of a full chunk
   double kap_limit;    // max_curvature when the optional curvature mask is on, +inf otherwise
-};
-
-// Shared-memory carve-up (byte offsets, 16-byte aligned), used by the host for the launch size too.
-struct GridLayout {
-  uint32_t spline, oc, obs, bbox, bbox_d, axes, lon, lat, lon_cost, lat_cost, dmax, lon_viol, lon_ncart, lon_E, npairs, pairs, cflags, masks,
-      listed, near_list, bytes;
+  GridLayout lay;      // shared-memory carve-up (host-computed: the offsets are then constant-bank operands)
+  int32_t row_len;     // slots * nv * n_pad: elements of one longitudinal table
 };
 
 __host__ __device__ inline uint32_t grid_align16(uint32_t v) { return (v + 15u) & ~15u; }
 
 __host__ __device__ inline GridLayout grid_layout(int Kp, int Mp, int E_stage, int nv, int d_chunk, int n_pad, int e_pad,
-                                                  int words) {
+                                                  int words, int slots) {
   GridLayout L;
+  const uint32_t lon_rows = (uint32_t)slots * nv, lat_rows = (uint32_t)slots * d_chunk;
   uint32_t o = 16;  // two mbarriers
   L.spline = o;     o += 9u * Kp * 8u;
   L.oc = o;         o += 4u * Mp * 8u;
-  L.obs = o;        o += (uint32_t)E_stage * 4u * Mp * 8u;
+  L.obs = o;        o += (uint32_t)E_stage * 2u * Mp * 8u;
   L.bbox = o;       o += (uint32_t)e_pad * 4u * 8u;
   L.bbox_d = o;     o += (uint32_t)e_pad * 4u * 8u;
   L.axes = o;       o += 4u * kAxisMax * 8u;
-  L.lon = o;        o += 5u * nv * n_pad * 8u;
-  L.lat = o;        o += (uint32_t)d_chunk * n_pad * 8u;
-  L.lon_cost = o;   o += grid_align16(nv * 8u);
-  L.lat_cost = o;   o += grid_align16(d_chunk * 8u);
+  L.slot_d = o;     o += 2u * kMaxSlots * 8u * 8u;   // [2][kMaxSlots][8]: ego state (6), T, n -- double-buffered by item parity
+  L.slot_base = o;  o += 2u * kMaxSlots * 8u;        // [2][kMaxSlots] id of the slot's candidate (i0, 0, k)
+  L.slot_off = o;   o += 2u * kMaxSlots * 4u;        // [2][kMaxSlots] the same relative to slot 0, in output elements
+  L.lon = o;        o += 5u * lon_rows * n_pad * 8u;
+  L.lat = o;        o += lat_rows * n_pad * 8u;
+  L.lon_cost = o;   o += grid_align16(lon_rows * 8u);
+  L.lat_cost = o;   o += grid_align16(lat_rows * 8u);
   L.dmax = o;       o += 16;
-  L.lon_viol = o;   o += grid_align16(nv * 4u);
-  L.lon_ncart = o;  o += grid_align16(nv * 4u);
-  L.lon_E = o;      o += grid_align16(nv * 4u);
-  L.npairs = o;     o += 16;
-  L.pairs = o;      o += grid_align16((uint32_t)nv * e_pad * 4u);
-  L.cflags = o;     o += grid_align16((uint32_t)d_chunk * nv * 4u);
-  L.masks = o;      o += grid_align16((uint32_t)nv * e_pad * words * 4u);
-  L.listed = o;     o += grid_align16((uint32_t)nv * e_pad * 4u);
+  L.lon_viol = o;   o += grid_align16(lon_rows * 4u);
+  L.lon_ncart = o;  o += grid_align16(lon_rows * 4u);
+  L.lon_E = o;      o += grid_align16(lon_rows * 4u);
+  L.counters = o;   o += 16;
+  L.pairs = o;      o += grid_align16(lon_rows * e_pad * 4u);
+  L.cflags = o;     o += grid_align16(lat_rows * nv * 4u);
+  L.masks = o;      o += grid_align16(lon_rows * e_pad * words * 4u);
+  L.listed = o;     o += grid_align16(lon_rows * e_pad * 4u);
   L.near_list = o;  o += grid_align16((uint32_t)e_pad * Mp * 4u);
   L.bytes = o;
   return L;
@@ -231,31 +242,35 @@ __global__ void __launch_bounds__(kGridThreads, kGridMinCtas) fiss_grid_kernel(c
   long long phase_t = clock64();
 #endif
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  const GridLayout L = grid_layout(a.Kp, a.Mp, a.E_stage, a.nv, a.d_chunk, a.n_pad, a.e_pad, a.words);
+  const GridLayout& L = a.lay;
   uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw);  // [0] spline, [1] obstacles
   double* sp = reinterpret_cast<double*>(smem_raw + L.spline);
   double* oc = reinterpret_cast<double*>(smem_raw + L.oc);
-  double* obs_s = reinterpret_cast<double*>(smem_raw + L.obs);
+  double* obs_s = reinterpret_cast<double*>(smem_raw + L.obs);  // [E_stage][2][Mp]: centres of the checked steps
   // [e_pad][4]: x_min, x_max, y_min, y_max of the frame points of the rows that check a step, as order-preserving keys
   unsigned long long* bbox_key = reinterpret_cast<unsigned long long*>(smem_raw + L.bbox);
+  double* bbox = reinterpret_cast<double*>(smem_raw + L.bbox_d);  // the same boxes as doubles (decoded keys)
   double* ax = reinterpret_cast<double*>(smem_raw + L.axes);
+  double* slot_d = reinterpret_cast<double*>(smem_raw + L.slot_d);
+  long long* slot_base = reinterpret_cast<long long*>(smem_raw + L.slot_base);
+  int32_t* slot_off = reinterpret_cast<int32_t*>(smem_raw + L.slot_off);
   double* lon = reinterpret_cast<double*>(smem_raw + L.lon);
-  double* lat = reinterpret_cast<double*>(smem_raw + L.lat);
+  double* lat = reinterpret_cast<double*>(smem_raw + L.lat);  // [slots * d_chunk][n_pad] lateral offsets d(t)
   double* lon_cost = reinterpret_cast<double*>(smem_raw + L.lon_cost);
   double* lat_cost = reinterpret_cast<double*>(smem_raw + L.lat_cost);
   unsigned long long* dmax_bits = reinterpret_cast<unsigned long long*>(smem_raw + L.dmax);
   uint32_t* lon_viol = reinterpret_cast<uint32_t*>(smem_raw + L.lon_viol);
   int32_t* lon_ncart = reinterpret_cast<int32_t*>(smem_raw + L.lon_ncart);
   int32_t* lon_E = reinterpret_cast<int32_t*>(smem_raw + L.lon_E);        // checked steps of the row
-  uint32_t* npairs = reinterpret_cast<uint32_t*>(smem_raw + L.npairs);    // length of the work list
+  uint32_t* npairs = reinterpret_cast<uint32_t*>(smem_raw + L.counters);  // length of the work list
+  uint32_t* n_near = npairs + 1;     // length of near_list
+  uint32_t* rows_done = npairs + 2;  // longitudinal rows of the item that have folded their frame points into the boxes
+  uint32_t* row_task = npairs + 3;   // next row task of stage A
   uint32_t* pairs = reinterpret_cast<uint32_t*>(smem_raw + L.pairs);      // (row << 16 | checked step) with any proximity bit
   uint32_t* cflags = reinterpret_cast<uint32_t*>(smem_raw + L.cflags);    // per candidate: collision / curvature bits
   uint32_t* masks = reinterpret_cast<uint32_t*>(smem_raw + L.masks);
   uint32_t* listed = reinterpret_cast<uint32_t*>(smem_raw + L.listed);        // (row, step) already on the work list
   uint32_t* near_list = reinterpret_cast<uint32_t*>(smem_raw + L.near_list);  // (step << 16 | obstacle) that passed the box
-  uint32_t* n_near = npairs + 1;
-  uint32_t* rows_done = npairs + 2;  // longitudinal rows of the item that have folded their frame points into the boxes
-  double* bbox = reinterpret_cast<double*>(smem_raw + L.bbox_d);  // [e_pad][4]: the boxes as doubles (decoded keys)
 
   const fiss_params& p = a.p;
   const int warp = threadIdx.x >> 5;
@@ -263,10 +278,14 @@ __global__ void __launch_bounds__(kGridThreads, kGridMinCtas) fiss_grid_kernel(c
   const int wpc = blockDim.x >> 5;
   const int n_pad = a.n_pad;
   const int Mp = a.Mp;
-  const int row_len = a.nv * n_pad;  // one longitudinal table
-  double2* P2 = reinterpret_cast<double2*>(lon);                // [nv][n_pad] frame point (px, py)
-  double2* U2 = reinterpret_cast<double2*>(lon + 2 * row_len);  // [nv][n_pad] unit tangent (ux, uy)
-  double* SD = lon + 4 * row_len;                               // [nv][n_pad] longitudinal speed
+  const int nv = a.nv;
+  const int G = a.slots;
+  const int dc = a.d_chunk;
+  // "longitudinal row" jj = g * nv + j and "lateral row" ll = g * d_chunk + ii number the rows of all slots of an item
+  const int row_len = a.row_len;  // one longitudinal table
+  double2* P2 = reinterpret_cast<double2*>(lon);                // [slots * nv][n_pad] frame point (px, py)
+  double2* U2 = reinterpret_cast<double2*>(lon + 2 * row_len);  // [slots * nv][n_pad] unit tangent (ux, uy)
+  double* SD = lon + 4 * row_len;                               // [slots * nv][n_pad] longitudinal speed
 
   // ---- stage 0: tables.  The spline is needed first (stage A); the obstacle rows only in stage A'.
   if (threadIdx.x == 0) {
@@ -275,7 +294,8 @@ __global__ void __launch_bounds__(kGridThreads, kGridMinCtas) fiss_grid_kernel(c
     fence_mbar_init();
   }
   __syncthreads();
-  const uint32_t row_bytes = 4u * Mp * 8u;
+  const uint32_t const_bytes = 4u * Mp * 8u;
+  const uint32_t row_bytes = 2u * Mp * 8u;  // cx, cy of one step: the first two components of a table row
   int rows_live = 0;  // staged rows that exist in the table (time < T_obs)
   for (int e = 0; e < a.E_stage; ++e)
     if (p.time_step_now + e * p.check_res < a.T_obs) rows_live = e + 1;
@@ -283,28 +303,26 @@ __global__ void __launch_bounds__(kGridThreads, kGridMinCtas) fiss_grid_kernel(c
     const uint32_t spline_bytes = 9u * a.Kp * 8u;
     mbar_expect_tx(&bar[0], spline_bytes);
     bulk_g2s(sp, a.spline, spline_bytes, &bar[0]);
-    mbar_expect_tx(&bar[1], (Mp > 0 ? row_bytes : 0u) + (uint32_t)rows_live * row_bytes);
-    if (Mp > 0) bulk_g2s(oc, a.obs_const, row_bytes, &bar[1]);
+    mbar_expect_tx(&bar[1], (Mp > 0 ? const_bytes : 0u) + (uint32_t)rows_live * row_bytes);
+    if (Mp > 0) bulk_g2s(oc, a.obs_const, const_bytes, &bar[1]);
     for (int e = 0; e < rows_live; ++e)
-      bulk_g2s(obs_s + (int64_t)e * 4 * Mp, a.obs_tab + (int64_t)(p.time_step_now + e * p.check_res) * 4 * Mp,
+      bulk_g2s(obs_s + (int64_t)e * 2 * Mp, a.obs_tab + (int64_t)(p.time_step_now + e * p.check_res) * 4 * Mp,
                row_bytes, &bar[1]);
   }
   // staged rows past the end of the predictions: nobody has a state there (state_at_time -> None)
-  for (int64_t q = (int64_t)rows_live * 4 * Mp + threadIdx.x; q < (int64_t)a.E_stage * 4 * Mp; q += blockDim.x)
-    obs_s[q] = (((q / Mp) & 3) < 2) ? kObsFar : 0.0;
+  for (int64_t q = (int64_t)rows_live * 2 * Mp + threadIdx.x; q < (int64_t)a.E_stage * 2 * Mp; q += blockDim.x)
+    obs_s[q] = kObsFar;
   for (int q = threadIdx.x; q < 4 * kAxisMax; q += blockDim.x) ax[q] = a.axes[q];
-  mbar_wait(&bar[0], 0);
-  mbar_wait(&bar[1], 0);
-  __syncthreads();
-  FISS_PHASE(0);
 
-  const double* obs = a.E_stage > 0 ? obs_s : a.obs_tab;
-  const int obs_row0 = a.E_stage > 0 ? 0 : p.time_step_now;
-  const int obs_row_step = a.E_stage > 0 ? 1 : p.check_res;
+  // centres (cx, cy) of checked step e: staged rows, or the global table
+  const double* obs = a.E_stage > 0 ? obs_s : a.obs_tab + (int64_t)p.time_step_now * 4 * Mp;
+  const int obs_pitch = a.E_stage > 0 ? 2 * Mp : p.check_res * 4 * Mp;
+  // (cos, sin) of the obstacles at checked step e: always the global table (only the exact predicate reads them)
+  const double* obs_cs = a.obs_tab + (int64_t)p.time_step_now * 4 * Mp + 2 * Mp;
+  const int cs_pitch = p.check_res * 4 * Mp;
   const double hle = 0.5 * p.ego_length, hwe = 0.5 * p.ego_width;
   const double re = sqrt(hle * hle + hwe * hwe);
 
-  const int nv = a.nv;
   const uint32_t nv_magic = a.nv_magic;  // c / nv == (c * magic) >> 20 for c < 2^20 / nv
   const int e_pad = a.e_pad;
   const int words = a.words;
@@ -312,6 +330,7 @@ __global__ void __launch_bounds__(kGridThreads, kGridMinCtas) fiss_grid_kernel(c
   const int t_left = a.final_time_step - p.time_step_now;
   const uint32_t n_items = (uint32_t)a.items;
   const uint32_t n_chunks = (uint32_t)a.n_chunks, nt = (uint32_t)a.nt;
+  const uint32_t n_bk = (uint32_t)a.B * nt;  // (ego, horizon) pairs of the launch
 
   // Per-item state of stage A' / B: empty boxes (+inf, -inf: infinitely far from everything), clear masks, list marks
   // and counters.  Runs before the first item and inside stage C of every item (which is the only reader of cflags and
@@ -322,38 +341,77 @@ __global__ void __launch_bounds__(kGridThreads, kGridMinCtas) fiss_grid_kernel(c
       *npairs = 0u;
       *n_near = 0u;
       *rows_done = 0u;
+      *row_task = 0u;
     }
     for (int q = threadIdx.x; q < 4 * e_pad; q += blockDim.x) bbox_key[q] = order_key((q & 1) ? -CUDART_INF : CUDART_INF);
-    for (int q = threadIdx.x; q < nv * e_pad; q += blockDim.x) listed[q] = 0u;
-    for (int q = threadIdx.x; q < nv * e_pad * words; q += blockDim.x) masks[q] = 0u;
+    for (int q = threadIdx.x; q < G * nv * e_pad; q += blockDim.x) listed[q] = 0u;
+    for (int q = threadIdx.x; q < G * nv * e_pad * words; q += blockDim.x) masks[q] = 0u;
+  };
+  // The slots of an item: ego state, horizon, step count, output ids -- fetched one item ahead (the global loads are
+  // in flight while the previous item finishes), double-buffered by the parity of the CTA's item count.
+  auto load_slots = [&](uint32_t item, int par) {
+    if (threadIdx.x < (unsigned)(8 * G) && item < n_items) {
+      const int g = threadIdx.x >> 3, q = threadIdx.x & 7;
+      const uint32_t bk0 = (item / n_chunks) * (uint32_t)G;
+      const uint32_t chunk = item - (item / n_chunks) * n_chunks;
+      const uint32_t bk = bk0 + (uint32_t)g;
+      if (bk < n_bk) {
+        const uint32_t b = bk / nt, k = bk - b * nt;
+        double v;
+        if (q < 6) v = a.ego[6 * (int64_t)b + q];
+        else v = a.axes[(q - 4) * kAxisMax + k];  // q = 6: T, q = 7: n
+        slot_d[(par * kMaxSlots + g) * 8 + q] = v;
+        if (q == 0) {
+          const uint32_t b0 = bk0 / nt, k0 = bk0 - b0 * nt;
+          const long long i_off = (long long)chunk * dc * a.sd;
+          const long long base = (long long)b * a.C + i_off + (long long)k * a.st;
+          const long long base0 = (long long)b0 * a.C + i_off + (long long)k0 * a.st;
+          slot_base[par * kMaxSlots + g] = base;
+          slot_off[par * kMaxSlots + g] = (int32_t)((base - base0) * a.n_stride);
+        }
+      }
+    }
   };
   reset_item_state();
-  for (int q = threadIdx.x; q < a.d_chunk * nv; q += blockDim.x) cflags[q] = 0u;
+  for (int q = threadIdx.x; q < G * dc * nv; q += blockDim.x) cflags[q] = 0u;
+  load_slots(blockIdx.x, 0);
+  mbar_wait(&bar[0], 0);  // the obstacle rows are waited for where stage A' first needs them
+  __syncthreads();
+  FISS_PHASE(0);
 
-  for (uint32_t item = blockIdx.x; item < n_items; item += gridDim.x) {
-    const uint32_t bk = item / n_chunks;
-    const int chunk = (int)(item - bk * n_chunks);
-    const int b = (int)(bk / nt);
-    const int k = (int)(bk - (uint32_t)b * nt);
-    const int i0 = chunk * a.d_chunk;
-    const int rows_i = min(a.d_chunk, a.nd - i0);
-    const int n_cand = rows_i * nv;
+  int par = 0;
+  for (uint32_t item = blockIdx.x; item < n_items; item += gridDim.x, par ^= 1) {
+    const uint32_t bk0 = (item / n_chunks) * (uint32_t)G;
+    const int chunk = (int)(item - (item / n_chunks) * n_chunks);
+    const int Gv = (int)min((uint32_t)G, n_bk - bk0);  // slots of this item (the last item may be short)
+    const int i0 = chunk * dc;
+    const int rows_i = min(dc, a.nd - i0);
+    const int n_lon = Gv * nv;
+    const double* sl = slot_d + par * kMaxSlots * 8;
 
-    // the per-item state was reset before the loop / by the previous item's stage C; this barrier also means the
-    // previous item's readers are done with the tables
+    // the per-item state was reset before the loop / by the previous item's stage C, which also fetched this item's
+    // slots; this barrier also means the previous item's readers are done with the tables
     __syncthreads();
-    const double T = ax[2 * kAxisMax + k];
-    const int n = (int)ax[3 * kAxisMax + k];
-    const double* ego = a.ego + 6 * (int64_t)b;
-    const double s0 = ego[0], v0 = ego[1], a0 = ego[2], d0 = ego[3], dv0 = ego[4], da0 = ego[5];
-    const double T2 = T * T, T3 = T2 * T;
+    // last item of this CTA: a dependent launch (the record kernel, fiss_pick_winners_dev) may start staging its tables
+    if (item + gridDim.x >= n_items) pdl_launch_dependents();
     FISS_PHASE(1);
 
-    // ---- stage A: one warp per row
-    for (int task = warp; task < nv + rows_i; task += wpc) {
-      if (task < nv) {
+    // ---- stage A: one warp per row, rows dealt dynamically (the longitudinal rows, ~3x the work of a lateral row,
+    // go first)
+    for (;;) {
+      int task = 0;
+      if (lane == 0) task = (int)atomicAdd(row_task, 1u);
+      task = __shfl_sync(kFull, task, 0);
+      if (task >= n_lon + Gv * rows_i) break;
+      if (task < n_lon) {
         // longitudinal quartic, end (v_end, 0)                      polynomial.py:5-19 (SURVEY A.2 closed form)
-        const int j = task;
+        const int jj = task;
+        const int g = (int)(((uint32_t)jj * nv_magic) >> 20);
+        const int j = jj - g * nv;
+        const double s0 = sl[8 * g + 0], v0 = sl[8 * g + 1], a0 = sl[8 * g + 2];
+        const double T = sl[8 * g + 6];
+        const int n = (int)sl[8 * g + 7];
+        const double T2 = T * T, T3 = T2 * T;
         const double v_end = ax[kAxisMax + j];
         const double qa2 = 0.5 * a0;
         const double Vq = v_end - v0 - 2.0 * qa2 * T;
@@ -363,7 +421,7 @@ __global__ void __launch_bounds__(kGridThreads, kGridMinCtas) fiss_grid_kernel(c
         double acc = 0.0;
         unsigned viol = 0;
         int first_bad = n;
-        const int base = j * n_pad;
+        const int base = jj * n_pad;
         // Two time steps per lane (m and m + 32) in lockstep: two independent dependency chains through the
         // polynomials, the segment search and the frame -- a row is one warp's serial work, so its latency is the
         // stage's.  The accumulation order (m, then m + 32, then m + 64 ...) is the one-step-per-pass order.
@@ -416,10 +474,10 @@ __global__ void __launch_bounds__(kGridThreads, kGridMinCtas) fiss_grid_kernel(c
         const bool do_coll = a.M > 0 && horizon > 0 && n_cart >= 2 && (p.collide_all || viol == 0);
         const int E_row = do_coll ? (horizon + res - 1) / res : 0;
         if (lane == 0) {
-          lon_cost[j] = acc;
-          lon_viol[j] = viol;
-          lon_ncart[j] = n_cart;
-          lon_E[j] = E_row;
+          lon_cost[jj] = acc;
+          lon_viol[jj] = viol;
+          lon_ncart[jj] = n_cart;
+          lon_E[jj] = E_row;
         }
         // frame points from the truncation on (and the pad) are NaN: the materialisation reads them without a test and
         // x, y, heading and curvature of the steps outside the Cartesian part come out NaN by propagation
@@ -442,13 +500,20 @@ __global__ void __launch_bounds__(kGridThreads, kGridMinCtas) fiss_grid_kernel(c
           __threadfence_block();
           arrived = atomicAdd(rows_done, 1u);
         }
-        if (__shfl_sync(kFull, arrived, 0) == (unsigned)nv - 1u) {
+        if (__shfl_sync(kFull, arrived, 0) == (unsigned)n_lon - 1u) {
           __threadfence_block();
           for (int q = lane; q < 4 * e_pad; q += 32) bbox[q] = order_value(bbox_key[q]);
         }
       } else {
         // lateral quintic, end (d_end, 0, 0)                        polynomial.py:45-62
-        const int ii = task - nv;
+        const int lt = task - n_lon;
+        const int g = lt / rows_i;
+        const int ii = lt - g * rows_i;
+        const int ll = g * dc + ii;
+        const double d0 = sl[8 * g + 3], dv0 = sl[8 * g + 4], da0 = sl[8 * g + 5];
+        const double T = sl[8 * g + 6];
+        const int n = (int)sl[8 * g + 7];
+        const double T2 = T * T;
         const double d_end = ax[i0 + ii];
         const double iT = 1.0 / T;
         const double iT2 = iT * iT, iT3 = iT2 * iT;
@@ -460,7 +525,7 @@ __global__ void __launch_bounds__(kGridThreads, kGridMinCtas) fiss_grid_kernel(c
         const double la4 = (-15.0 * Dl + 7.0 * Vl * T - Al * T2) * (iT3 * iT);
         const double la5 = (6.0 * Dl - 3.0 * Vl * T + 0.5 * Al * T2) * (iT3 * iT2);
         double acc = 0.0, dmax = 0.0;
-        const int base = ii * n_pad;
+        const int base = ll * n_pad;
         for (int m0 = lane; m0 < n; m0 += 64) {  // two steps per lane in lockstep, same accumulation order
           const int m1 = m0 + 32;
           const bool has1 = m1 < n;
@@ -486,7 +551,7 @@ __global__ void __launch_bounds__(kGridThreads, kGridMinCtas) fiss_grid_kernel(c
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) dmax = fmax(dmax, __shfl_xor_sync(kFull, dmax, o));
         if (lane == 0) {
-          lat_cost[ii] = acc;
+          lat_cost[ll] = acc;
           atomicMax(dmax_bits, (unsigned long long)__double_as_longlong(dmax));  // non-negative doubles order as integers
         }
       }
@@ -494,50 +559,59 @@ __global__ void __launch_bounds__(kGridThreads, kGridMinCtas) fiss_grid_kernel(c
     __syncthreads();
     FISS_PHASE(2);
 
-    // ---- stage A': proximity masks.  masks[j][e] gets a bit per obstacle whose centre is within
-    // (max|d| + r_ego + r_obs) of the frame point of longitudinal row j at checked step e -- a superset of the
-    // obstacles any candidate on that row can touch there.  The per-step bounding boxes of the frame points were
-    // accumulated by the row warps of stage A; here
+    // ---- stage A': proximity masks.  masks[jj][e] gets a bit per obstacle whose centre is within
+    // (max|d| + r_ego + r_obs) of the frame point of longitudinal row jj at checked step e -- a superset of the
+    // obstacles any candidate on that row can touch there (max|d| over the lateral rows of the whole item).  The
+    // per-step bounding boxes of the frame points were accumulated by the row warps of stage A; here
     //   (1) one lane per (step, obstacle) tests the obstacle against the box (the same squared-distance expression
     //       as the per-row test, so the box can only over-accept); the few survivors go to a compact list;
     //   (2) one lane per (survivor, row) runs the per-row test, sets the mask bit and -- the first one to touch a
     //       (row, step) -- appends it to the work list of stage B.
     if (a.M > 0) {
+      mbar_wait(&bar[1], 0);  // obstacle rows landed (phase 0 completes once: later items pass straight through)
       const double dmax = __longlong_as_double((long long)*dmax_bits);
       const double reach0 = (dmax + re) * (1.0 + 1.0e-9) + 1.0e-9;
-      const uint32_t mp_magic = a.mp_magic;  // q / Mp for q < 2^20 / Mp
-      for (int q = threadIdx.x; q < e_pad * Mp; q += blockDim.x) {
-        const int e = (int)(((uint32_t)q * mp_magic) >> 20);
-        const int jo = q - e * Mp;
-        const int row = obs_row0 + e * obs_row_step;
-        const bool in_tab = a.E_stage > 0 ? e < a.E_stage : row < a.T_obs;
-        if (jo < a.M && in_tab) {
-          const double* slot = obs + row * (4 * Mp) + jo;
-          const double ox = slot[0], oy = slot[Mp];
-          const double reach = reach0 + oc[2 * Mp + jo] * (1.0 + 1.0e-9);
-          const double2 box_x = *reinterpret_cast<const double2*>(bbox + 4 * e);
-          const double2 box_y = *reinterpret_cast<const double2*>(bbox + 4 * e + 2);
-          const double bx = fmax(fmax(box_x.x - ox, ox - box_x.y), 0.0);
-          const double by = fmax(fmax(box_y.x - oy, oy - box_y.y), 0.0);
-          if (near2(bx, by) <= reach * reach) near_list[atomicAdd(n_near, 1u)] = ((uint32_t)e << 16) | (uint32_t)jo;
+      // lanes = obstacles (their reach is per-lane state), warps stride over the checked steps; with fewer than 32
+      // obstacle slots a warp packs 32 / Mp steps per pass
+      const int jl = lane & (min(Mp, 32) - 1);
+      const int e_sub = lane >> a.mp_shift;
+      const int steps_per_pass = 32 >> a.mp_shift;
+      for (int jb = 0; jb < Mp; jb += 32) {
+        const int jo = jb + jl;
+        const double reach = reach0 + oc[2 * Mp + jo] * (1.0 + 1.0e-9);
+        const double reach2 = reach * reach;
+        for (int e = warp * steps_per_pass + e_sub; e < e_pad; e += wpc * steps_per_pass) {
+          const bool in_tab = a.E_stage > 0 ? e < a.E_stage : p.time_step_now + e * res < a.T_obs;
+          if (jo < a.M && in_tab) {
+            const double* slot = obs + e * obs_pitch + jo;
+            const double ox = slot[0], oy = slot[Mp];
+            const double2 box_x = *reinterpret_cast<const double2*>(bbox + 4 * e);
+            const double2 box_y = *reinterpret_cast<const double2*>(bbox + 4 * e + 2);
+            // distance to the box per axis: max(lo - o, o - hi, 0), each value one of the differences (or 0)
+            const double xl = box_x.x - ox, xh = ox - box_x.y, yl = box_y.x - oy, yh = oy - box_y.y;
+            double bx = xh > xl ? xh : xl, by = yh > yl ? yh : yl;
+            bx = bx > 0.0 ? bx : 0.0;
+            by = by > 0.0 ? by : 0.0;
+            if (near2(bx, by) <= reach2) near_list[atomicAdd(n_near, 1u)] = ((uint32_t)e << 16) | (uint32_t)jo;
+          }
         }
       }
       __syncthreads();
       FISS_PHASE(4);
-      const uint32_t n_cand_pairs = *n_near * (uint32_t)nv;
+      const uint32_t n_cand_pairs = *n_near * (uint32_t)n_lon;
       for (uint32_t q = threadIdx.x; q < n_cand_pairs; q += blockDim.x) {
-        const uint32_t c = q / (uint32_t)nv;
-        const int j = (int)(q - c * (uint32_t)nv);
+        const uint32_t c = q / (uint32_t)n_lon;
+        const int jj = (int)(q - c * (uint32_t)n_lon);
         const uint32_t ej = near_list[c];
         const int e = (int)(ej >> 16), jo = (int)(ej & 0xffffu);
-        if (e < lon_E[j]) {
-          const double* slot = obs + (obs_row0 + e * obs_row_step) * (4 * Mp) + jo;
-          const double2 fp = P2[j * n_pad + e * res];
+        if (e < lon_E[jj]) {
+          const double* slot = obs + e * obs_pitch + jo;
+          const double2 fp = P2[jj * n_pad + e * res];
           const double reach = reach0 + oc[2 * Mp + jo] * (1.0 + 1.0e-9);
           if (near2(slot[0] - fp.x, slot[Mp] - fp.y) <= reach * reach) {
-            atomicOr(&masks[(j * e_pad + e) * words + (jo >> 5)], 1u << (jo & 31));
-            if (atomicExch(&listed[j * e_pad + e], 1u) == 0u)
-              pairs[atomicAdd(npairs, 1u)] = ((uint32_t)j << 16) | (uint32_t)e;
+            atomicOr(&masks[(jj * e_pad + e) * words + (jo >> 5)], 1u << (jo & 31));
+            if (atomicExch(&listed[jj * e_pad + e], 1u) == 0u)
+              pairs[atomicAdd(npairs, 1u)] = ((uint32_t)jj << 16) | (uint32_t)e;
           }
         }
       }
@@ -546,54 +620,54 @@ __global__ void __launch_bounds__(kGridThreads, kGridMinCtas) fiss_grid_kernel(c
     FISS_PHASE(5);
 
     // ---- stage B, collision (has_collision, frenet_optimal_planner.py:168-195): one lane per
-    // (lateral row, listed (row, step) pair); exact predicate on the listed obstacles only
+    // (lateral row of the pair's slot, listed (row, step) pair); exact predicate on the listed obstacles only
     {
       const uint32_t n_pairs = *npairs;
       const uint32_t n_work = (uint32_t)rows_i * n_pairs;
       const uint32_t np_magic = n_pairs ? 0xffffffffu / n_pairs + 1u : 0u;  // w / n_pairs == umulhi(w, magic), w < 2^32 / n_pairs
       for (uint32_t wk = threadIdx.x; wk < n_work; wk += blockDim.x) {
-        {
-          const int ii = n_pairs == 1u ? (int)wk : (int)__umulhi(wk, np_magic);
-          const uint32_t q = wk - (uint32_t)ii * n_pairs;
-          const double* Dr = lat + ii * n_pad;
-          const uint32_t pr = pairs[q];
-          const int j = (int)(pr >> 16), e = (int)(pr & 0xffffu);
-          const double2* pP = P2 + j * n_pad;
-          const double2* pU = U2 + j * n_pad;
-          // ego pose at checked step i = e*check_res: centre (x_i, y_i), heading of segment min(i, n'-2)
-          const int i = e * res;
-          const int seg = min(i, lon_ncart[j] - 2);
-          double xa, ya, xb, yb;
-          grid_pos(pP, pU, Dr, seg, xa, ya);
-          grid_pos(pP, pU, Dr, seg + 1, xb, yb);
-          const double dxs = xb - xa, dys = yb - ya;
-          const double h2 = dxs * dxs + dys * dys;
-          double c, s;
-          if (h2 > 0.0 && h2 < 1.0e300) {
-            const double r = rsqrt(h2);  // cos/sin of atan2(dy, dx) without the round trip
-            c = dxs * r;
-            s = dys * r;
-          } else {
-            sincos(atan2(dys, dxs), &s, &c);
-          }
-          const double ex = i == seg ? xa : xb, ey = i == seg ? ya : yb;
-          const double* orow = obs + (obs_row0 + e * obs_row_step) * (4 * Mp);
-          const uint32_t* mw = masks + (j * e_pad + e) * words;
-          bool h = false;
-          for (int w = 0; w < words && !h; ++w) {
-            uint32_t bits = mw[w];
-            while (bits && !h) {
-              const int jo = w * 32 + __ffs(bits) - 1;
-              bits &= bits - 1;
-              const double* slot = orow + jo;
-              const double dx = slot[0] - ex, dy = slot[Mp] - ey;
-              const double thr = re + oc[2 * Mp + jo];
-              if (dx * dx + dy * dy <= thr * thr)
-                h = rect_sat(dx, dy, c, s, hle, hwe, slot[2 * Mp], slot[3 * Mp], oc[jo], oc[Mp + jo]);
-            }
-          }
-          if (h) atomicOr(&cflags[ii * nv + j], FISS_FLAG_COLLISION);
+        const int ii = n_pairs == 1u ? (int)wk : (int)__umulhi(wk, np_magic);
+        const uint32_t q = wk - (uint32_t)ii * n_pairs;
+        const uint32_t pr = pairs[q];
+        const int jj = (int)(pr >> 16), e = (int)(pr & 0xffffu);
+        const int g = (int)(((uint32_t)jj * nv_magic) >> 20);
+        const int ll = g * dc + ii;
+        const double* Dr = lat + ll * n_pad;
+        const double2* pP = P2 + jj * n_pad;
+        const double2* pU = U2 + jj * n_pad;
+        // ego pose at checked step i = e*check_res: centre (x_i, y_i), heading of segment min(i, n'-2)
+        const int i = e * res;
+        const int seg = min(i, lon_ncart[jj] - 2);
+        double xa, ya, xb, yb;
+        grid_pos(pP, pU, Dr, seg, xa, ya);
+        grid_pos(pP, pU, Dr, seg + 1, xb, yb);
+        const double dxs = xb - xa, dys = yb - ya;
+        const double h2 = dxs * dxs + dys * dys;
+        double c, s;
+        if (h2 > 0.0 && h2 < 1.0e300) {
+          const double r = rsqrt(h2);  // cos/sin of atan2(dy, dx) without the round trip
+          c = dxs * r;
+          s = dys * r;
+        } else {
+          sincos(atan2(dys, dxs), &s, &c);
         }
+        const double ex = i == seg ? xa : xb, ey = i == seg ? ya : yb;
+        const double* orow = obs + e * obs_pitch;
+        const double* crow = obs_cs + (int64_t)e * cs_pitch;
+        const uint32_t* mw = masks + (jj * e_pad + e) * words;
+        bool h = false;
+        for (int w = 0; w < words && !h; ++w) {
+          uint32_t bits = mw[w];
+          while (bits && !h) {
+            const int jo = w * 32 + __ffs(bits) - 1;
+            bits &= bits - 1;
+            const double dx = orow[jo] - ex, dy = orow[Mp + jo] - ey;
+            const double thr = re + oc[2 * Mp + jo];
+            if (dx * dx + dy * dy <= thr * thr)
+              h = rect_sat(dx, dy, c, s, hle, hwe, crow[jo], crow[Mp + jo], oc[jo], oc[Mp + jo]);
+          }
+        }
+        if (h) atomicOr(&cflags[ll * nv + (jj - g * nv)], FISS_FLAG_COLLISION);
       }
     }
 
@@ -602,101 +676,97 @@ __global__ void __launch_bounds__(kGridThreads, kGridMinCtas) fiss_grid_kernel(c
     FISS_PHASE(6);
 #endif
     // ---- stage B, materialisation (calc_global_paths, frenet_optimal_planner.py:121-134).
-    // Lanes = flattened (longitudinal row j, time step m) elements f = j*n_stride + m of the frame tables, cut into
+    // Lanes = flattened (longitudinal row jj, time step m) elements f = jj*n_stride + m of the frame tables, cut into
     // blocks of 31 outputs: the 32nd lane of a block only supplies the heading of the next step (kappa_m needs
-    // yaw_{m+1}), so blocks are independent.  A task = (block, group of kMatRows lateral rows): the lane loads its two
-    // frame points (4 x LDS.128) and the speed once and walks the lateral rows of the group with them -- per
-    // lateral row two table reads, the position, the heading (polynomial atan2, csrc/fiss_math.cuh) and 1/ds; five
-    // coalesced stores.  The rows of a group are independent instruction chains (the loop is unrolled), which
-    // is what hides the FP64 latency at 2-3 resident CTAs per SM.
+    // yaw_{m+1}), so blocks are independent.  A task = (block, group of kMatRows lateral rows of the lane's slot): the
+    // lane loads its two frame points (4 x LDS.128) and advances the heading chains of the group's rows in lockstep
+    // (mat_rows); five coalesced stores per row.
     if (kYaw) {
       const int ns = a.n_stride;
       const uint32_t ns_magic = a.ns_magic;  // f / ns for f < 2^20 / ns
-      const int n_blocks = (nv * ns + 30) / 31;
+      const int n_blocks = (n_lon * ns + 30) / 31;
       const int n_groups = (rows_i + kMatRows - 1) / kMatRows;
-      const uint32_t ng_magic = rows_i == a.d_chunk ? a.ng_magic : (1u << 20) / (uint32_t)n_groups + 1u;
+      const uint32_t ng_magic = rows_i == dc ? a.ng_magic : (1u << 20) / (uint32_t)n_groups + 1u;
       MatOut mo;
-      // the x field of candidate (i0, j = 0, k): uniform per item; the lanes add 32-bit element offsets
-      // (one candidate set's field is C * n_stride < 2^31 elements, checked by the host)
-      mo.f_x = a.mat ? a.mat + ((int64_t)b * a.C + (int64_t)i0 * a.sd + (int64_t)k * a.st) * ns : nullptr;
+      // the x field of slot 0's candidate (i0, j = 0, k): uniform per item; the lanes add 32-bit element offsets
+      // (the host checks that slots * C * n_stride < 2^31 elements)
+      mo.f_x = a.mat ? a.mat + slot_base[par * kMaxSlots] * ns : nullptr;
       mo.pitch = a.mat_pitch;
       mo.kap_limit = a.kap_limit;
       const int lat_pitch = a.sd * ns;
       const int lon_pitch = a.sv * ns;
-      // tasks t = blk * n_groups + grp, dealt to the warps as contiguous ranges: consecutive tasks of a warp mostly
-      // share their block, whose lane set-up (indices, predicates) is redone only when the block changes
+      // tasks t = blk * n_groups + grp.  A task recomputes its lane set-up from t (~35 issue slots against ~400 for its
+      // rows): state carried from task to task was spilled to local memory, and the loads of the spilled loop state
+      // were the longest stalls of the kernel.
+      // (Dealing the tasks through a shared counter instead of this static stride measured 4 % slower.)
       const int n_tasks = n_groups * n_blocks;
-      const int t_begin = (warp * n_tasks) / wpc, t_end = ((warp + 1) * n_tasks) / wpc;
-      int blk = (int)(((uint32_t)t_begin * ng_magic) >> 20);
-      int grp = t_begin - blk * n_groups;
-      bool fresh = true;
-      const double2* fp = P2;  // &P2[row j][segment]
-      int j = 0, seg = 0, off_jm = 0;
-      double sd_v = 0.0;
-      for (int t = t_begin; t < t_end; ++t) {
-        if (fresh) {
-          const int f = blk * 31 + lane;
-          j = min((int)(((uint32_t)f * ns_magic) >> 20), nv - 1);
-          const int m = f - j * ns;  // >= ns for the lanes past the end of the table
-          const int n_cart = lon_ncart[j];
-          const bool in_cart = m < n_cart;  // (n' <= n <= ns)
-          // yaw_m = atan2 of segment min(m, n'-2): the last point repeats the previous heading (:127-130).  Steps
-          // outside the Cartesian part read NaN frame points (stage A), and so does the neighbour of a lone point
-          // (n' == 1: yaw / ds / c stay empty, :121).
-          seg = in_cart ? max(min(m, n_cart - 2), 0) : min(m, n_pad - 2);
-          fp = P2 + j * n_pad + seg;
-          mo.has_seg = in_cart && n_cart >= 2;
-          mo.at_seg = m == seg;
-          mo.has_kap = m < n_cart - 1 && lane < 31;  // lane 31 only supplies the next heading
-          mo.writes = mo.f_x != nullptr && lane < 31 && m < ns;
+      for (int t = warp; t < n_tasks; t += wpc) {
+        const int blk = (int)(((uint32_t)t * ng_magic) >> 20);
+        const int grp = t - blk * n_groups;
+        const int f = blk * 31 + lane;
+        const int jj = min((int)(((uint32_t)f * ns_magic) >> 20), n_lon - 1);
+        const int m = f - jj * ns;  // >= ns for the lanes past the end of the table
+        const int g = (int)(((uint32_t)jj * nv_magic) >> 20);
+        const int j = jj - g * nv;
+        const int n = (int)sl[8 * g + 7];
+        const int n_cart = lon_ncart[jj];
+        const bool in_cart = m < n_cart;  // (n' <= n <= ns)
+        // yaw_m = atan2 of segment min(m, n'-2): the last point repeats the previous heading (:127-130).  Steps
+        // outside the Cartesian part read NaN frame points (stage A), and so does the neighbour of a lone point
+        // (n' == 1: yaw / ds / c stay empty, :121).
+        const int seg = in_cart ? max(min(m, n_cart - 2), 0) : min(m, n_pad - 2);
+        const double2* fp = P2 + jj * n_pad + seg;
+        mo.has_seg = in_cart && n_cart >= 2;
+        mo.at_seg = m == seg;
+        mo.has_kap = m < n_cart - 1 && lane < 31;  // lane 31 only supplies the next heading
+        mo.writes = mo.f_x != nullptr && lane < 31 && m < ns;
 #ifdef FISS_EXP_NOSTORE
-          mo.writes = mo.writes && a.B < 0;
+        mo.writes = mo.writes && a.B < 0;
 #endif
-          sd_v = m < n ? SD[j * n_pad + min(m, n_pad - 1)] : CUDART_NAN;
-          off_jm = j * lon_pitch + m;
-        }
+        const double sd_v = m < n ? SD[jj * n_pad + min(m, n_pad - 1)] : CUDART_NAN;
         const double2 Pa = fp[0], Pb = fp[1];
         const double2 Ua = fp[row_len], Ub = fp[row_len + 1];  // U2 = P2 + row_len
         const int i_first = grp * kMatRows;
-        const double* Dr = lat + i_first * n_pad + seg;
-        const int off = i_first * lat_pitch + off_jm;
-        uint32_t* cf = cflags + i_first * nv + j;
+        const int ll = g * dc + i_first;  // first lateral row of the group in the lane's slot
+        const double* Dr = lat + ll * n_pad + seg;
+        const int off = slot_off[par * kMaxSlots + g] + i_first * lat_pitch + j * lon_pitch + m;
+        uint32_t* cf = cflags + ll * nv + j;
         const int rows_here = min(kMatRows, rows_i - i_first);  // warp-uniform
         int r = 0;
         for (; r + kMatIlp <= rows_here; r += kMatIlp)
           mat_rows<kMatIlp>(mo, Pa, Ua, Pb, Ub, sd_v, Dr + r * n_pad, n_pad, off + r * lat_pitch, lat_pitch, cf + r * nv, nv);
         for (; r < rows_here; ++r)
           mat_rows<1>(mo, Pa, Ua, Pb, Ub, sd_v, Dr + r * n_pad, n_pad, off + r * lat_pitch, lat_pitch, cf + r * nv, nv);
-        fresh = false;
-        if (++grp == n_groups) {
-          grp = 0;
-          ++blk;
-          fresh = true;
-        }
       }
     }
     __syncthreads();
     FISS_PHASE(7);
 
-    // ---- stage C: one lane per candidate -- cost (cost_function.py:41-50) and the flags word
+    // ---- stage C: one lane per candidate -- cost (cost_function.py:41-50) and the flags word; then the reset of the
+    // per-item state and the fetch of the next item's slots
     {
-      const int64_t id_base = (int64_t)b * a.C + (int64_t)i0 * a.sd + (int64_t)k * a.st;
-      const double inv_n = 1.0 / (double)n;
-      const double cost_time = p.cost_time_offset - (n - 1) * p.tick_t;  // (10 - t_last), cost_function.py:42
+      const int n_cand = Gv * rows_i * nv;
       for (int cidx = threadIdx.x; cidx < n_cand; cidx += blockDim.x) {
-        const int ii = (int)(((uint32_t)cidx * nv_magic) >> 20);
-        const int j = cidx - ii * nv;
-        const int n_cart = lon_ncart[j];
-        const unsigned viol = lon_viol[j];
-        unsigned extra = cflags[cidx];
-        cflags[cidx] = 0u;
+        const int lt = (int)(((uint32_t)cidx * nv_magic) >> 20);  // lateral row among the item's Gv * rows_i
+        const int j = cidx - lt * nv;
+        const int g = lt / rows_i;
+        const int ii = lt - g * rows_i;
+        const int ll = g * dc + ii, jj = g * nv + j;
+        const int n = (int)sl[8 * g + 7];
+        const double inv_n = 1.0 / (double)n;
+        const double cost_time = p.cost_time_offset - (n - 1) * p.tick_t;  // (10 - t_last), cost_function.py:42
+        const int n_cart = lon_ncart[jj];
+        const unsigned viol = lon_viol[jj];
+        unsigned extra = cflags[ll * nv + j];
+        cflags[ll * nv + j] = 0u;
         // n' == 1 with obstacles: traj.yaw[0] raises inside the try => "collision" (:178-182)
         if (a.M > 0 && min(n_cart, t_left) > 0 && n_cart < 2 && (p.collide_all || viol == 0)) extra |= FISS_FLAG_COLLISION;
-        const int64_t out_id = id_base + ii * a.sd + j * a.sv;
-        a.cost[out_id] = (cost_time + (lon_cost[j] + lat_cost[ii])) * inv_n;
+        const int64_t out_id = slot_base[par * kMaxSlots + g] + ii * a.sd + j * a.sv;
+        a.cost[out_id] = (cost_time + (lon_cost[jj] + lat_cost[ll])) * inv_n;
         a.flags[out_id] = viol | extra | ((uint32_t)n_cart << FISS_FLAG_NCART_SHIFT);
       }
       reset_item_state();
+      load_slots(item + gridDim.x, par ^ 1);
     }
   }
 #ifdef FISS_PHASE_TIMING

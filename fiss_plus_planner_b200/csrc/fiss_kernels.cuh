@@ -65,7 +65,15 @@ struct EvalArgs {
   int32_t* pick_idx;           // [total] winner (-1: none)
   double* pick_best;           // [total] its cost (+inf: none)
   int32_t* pick_meta;          // [total][2] (n, n') of the winner, or NULL
+  // launched with programmatic stream serialisation behind the kernel that writes pick_cost / pick_flags: the CTAs
+  // stage their tables while that kernel drains and wait for its results only then
+  int32_t after_producer;
 };
+
+// Programmatic dependent launch (PTX griddepcontrol): a producer signals that its dependents may be scheduled; a
+// dependent waits until the producer grid has completed and its writes are visible.
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait_producer() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 
 // ------------------------------------------------------------------------------------------------
 // PTX wrappers: mbarrier + 1-D bulk TMA (SASS: SYNCS.* / UBLKCP)
@@ -502,6 +510,7 @@ __global__ void __launch_bounds__(kThreads) fiss_eval_kernel(const EvalArgs a) {
       obs_s[q] = (((q / a.Mp) & 3) < 2) ? kObsFar : 0.0;
   }
   mbar_wait(bar, 0);
+  if (kRec && a.after_producer) pdl_wait_producer();
   __syncthreads();
 
   const double* obs = a.obs_in_smem ? obs_s : a.obs_tab;
