@@ -339,7 +339,7 @@ int32_t eval_grid(fiss_handle* h, cudaStream_t st, const double* d_ego, int B, c
   const int64_t base_items = (int64_t)B * g->nt;
   const int64_t want = 2 * (int64_t)h->sm_count;
   int chunks = (int)std::min<int64_t>(g->nd, std::max<int64_t>(1, (want + base_items - 1) / base_items));
-  a.d_chunk = std::max(1, g->nd / chunks);
+  a.d_chunk = std::max(1, (g->nd + chunks - 1) / chunks);  // even chunks (33 rows in 2 chunks: 17 + 16, not 16 + 16 + 1)
   a.n_chunks = (g->nd + a.d_chunk - 1) / a.d_chunk;
   // obstacle rows (centres) of the checked steps go to shared memory while the CTA stays under the budget, else
   // they are read from global memory / L2
@@ -347,6 +347,7 @@ int32_t eval_grid(fiss_handle* h, cudaStream_t st, const double* d_ego, int B, c
   const int E_max = h->M > 0 ? (horizon + p->check_res - 1) / p->check_res : 0;
   const auto magic = [](int d) { return (1u << 20) / (uint32_t)std::max(d, 1) + 1u; };
   a.nv_magic = magic(a.nv);
+  a.nt_magic = a.nt > 1 ? 0xffffffffu / (uint32_t)a.nt + 1u : 0u;
   a.ns_magic = magic(n_stride);
   const int n_groups = (a.d_chunk + fiss::kMatRows - 1) / fiss::kMatRows;
   a.ng_magic = magic(n_groups);
@@ -359,7 +360,8 @@ int32_t eval_grid(fiss_handle* h, cudaStream_t st, const double* d_ego, int B, c
     // the kernel's multiply-shift divisions are exact below 2^20
     const int64_t lon_elems = (int64_t)a.slots * a.nv * n_stride + 32, n_blocks = (lon_elems + 30) / 31;
     const bool exact = lon_elems * n_stride < (1 << 20) && (int64_t)a.slots * a.d_chunk * a.nv * a.nv < (1 << 20) &&
-                       n_blocks * n_groups * n_groups < (1 << 20) && (int64_t)a.slots * a.C * n_stride < ((int64_t)1 << 31);
+                       n_blocks * n_groups * n_groups < (1 << 20) && (int64_t)a.slots * a.C * n_stride < ((int64_t)1 << 31) &&
+                       base_items * g->nt < ((int64_t)1 << 32);
     a.E_stage = E_max;
     L = fiss::grid_layout(a.Kp, a.Mp, a.E_stage, a.nv, a.d_chunk, a.n_pad, a.e_pad, a.words, a.slots);
     const bool supplied = slots_forced || base_items / a.slots >= 2 * (int64_t)fiss::kGridMinCtas * h->sm_count;
@@ -367,7 +369,7 @@ int32_t eval_grid(fiss_handle* h, cudaStream_t st, const double* d_ego, int B, c
       if (exact && supplied && L.bytes <= kSmemCtaBudget) break;
       continue;
     }
-    if (!exact) return fail(h, FISS_ERR_CAPACITY, "lattice too large for the kernel's index arithmetic (nv * n_stride^2 must stay below 2^20)");
+    if (!exact) return fail(h, FISS_ERR_CAPACITY, "lattice or batch too large for the kernel's index arithmetic (nv * n_stride^2 < 2^20, B * nt^2 < 2^32)");
     if (L.bytes > kSmemCtaBudget) {
       a.E_stage = 0;
       L = fiss::grid_layout(a.Kp, a.Mp, a.E_stage, a.nv, a.d_chunk, a.n_pad, a.e_pad, a.words, a.slots);

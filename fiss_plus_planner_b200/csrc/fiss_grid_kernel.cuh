@@ -101,6 +101,7 @@ struct GridArgs {
   int64_t mat_pitch;   // elements between two fields of the materialisation = B*C*n_stride
   // x / d == (x * magic(d)) >> 20 for x * d < 2^20 (host-computed: an integer division costs ~20 issue slots per warp)
   uint32_t nv_magic, ns_magic, ng_magic;  // d = nv, n_stride, groups of a full chunk
+  uint32_t nt_magic;   // x / nt == umulhi(x, nt_magic) for x < 2^32 / nt, nt > 1
   double kap_limit;    // max_curvature when the optional curvature mask is on, +inf otherwise
   GridLayout lay;      // shared-memory carve-up (host-computed: the offsets are then constant-bank operands)
   int32_t row_len;     // slots * nv * n_pad: elements of one longitudinal table
@@ -352,17 +353,18 @@ __global__ void __launch_bounds__(kGridThreads, kGridMinCtas) fiss_grid_kernel(c
   auto load_slots = [&](uint32_t item, int par) {
     if (threadIdx.x < (unsigned)(8 * G) && item < n_items) {
       const int g = threadIdx.x >> 3, q = threadIdx.x & 7;
-      const uint32_t bk0 = (item / n_chunks) * (uint32_t)G;
-      const uint32_t chunk = item - (item / n_chunks) * n_chunks;
+      const uint32_t iq = n_chunks == 1u ? item : item / n_chunks;
+      const uint32_t bk0 = iq * (uint32_t)G;
+      const uint32_t chunk = item - iq * n_chunks;
       const uint32_t bk = bk0 + (uint32_t)g;
       if (bk < n_bk) {
-        const uint32_t b = bk / nt, k = bk - b * nt;
+        const uint32_t b = nt == 1u ? bk : __umulhi(bk, a.nt_magic), k = bk - b * nt;
         double v;
         if (q < 6) v = a.ego[6 * (int64_t)b + q];
         else v = a.axes[(q - 4) * kAxisMax + k];  // q = 6: T, q = 7: n
         slot_d[(par * kMaxSlots + g) * 8 + q] = v;
         if (q == 0) {
-          const uint32_t b0 = bk0 / nt, k0 = bk0 - b0 * nt;
+          const uint32_t b0 = nt == 1u ? bk0 : __umulhi(bk0, a.nt_magic), k0 = bk0 - b0 * nt;
           const long long i_off = (long long)chunk * dc * a.sd;
           const long long base = (long long)b * a.C + i_off + (long long)k * a.st;
           const long long base0 = (long long)b0 * a.C + i_off + (long long)k0 * a.st;
@@ -381,8 +383,9 @@ __global__ void __launch_bounds__(kGridThreads, kGridMinCtas) fiss_grid_kernel(c
 
   int par = 0;
   for (uint32_t item = blockIdx.x; item < n_items; item += gridDim.x, par ^= 1) {
-    const uint32_t bk0 = (item / n_chunks) * (uint32_t)G;
-    const int chunk = (int)(item - (item / n_chunks) * n_chunks);
+    const uint32_t iq = n_chunks == 1u ? item : item / n_chunks;
+    const uint32_t bk0 = iq * (uint32_t)G;
+    const int chunk = (int)(item - iq * n_chunks);
     const int Gv = (int)min((uint32_t)G, n_bk - bk0);  // slots of this item (the last item may be short)
     const int i0 = chunk * dc;
     const int rows_i = min(dc, a.nd - i0);
@@ -698,9 +701,10 @@ __global__ void __launch_bounds__(kGridThreads, kGridMinCtas) fiss_grid_kernel(c
       // tasks t = blk * n_groups + grp.  A task recomputes its lane set-up from t (~35 issue slots against ~400 for its
       // rows): state carried from task to task was spilled to local memory, and the loads of the spilled loop state
       // were the longest stalls of the kernel.
-      // (Dealing the tasks through a shared counter instead of this static stride measured 4 % slower.)
+      // (Dealing the tasks through a shared counter instead of this static stride measured 4 % slower.)  The stride
+      // starts from the last warp: the low warps carry the extra pass of the collision stage above.
       const int n_tasks = n_groups * n_blocks;
-      for (int t = warp; t < n_tasks; t += wpc) {
+      for (int t = wpc - 1 - warp; t < n_tasks; t += wpc) {
         const int blk = (int)(((uint32_t)t * ng_magic) >> 20);
         const int grp = t - blk * n_groups;
         const int f = blk * 31 + lane;
