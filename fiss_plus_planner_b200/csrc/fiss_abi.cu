@@ -63,6 +63,7 @@ struct PinBuf {
   T* as() const { return static_cast<T*>(p); }
 };
 
+constexpr size_t kArenaBytesMax = 256 * 1024;  // plan_common: results up to this size travel as one block
 constexpr int kMaxParts = 4;                   // plan_common: pieces a big batch is pipelined in
 constexpr size_t kSmemLimit = 227 * 1024;      // opt-in maximum per CTA on sm_100
 constexpr size_t kSmemObsBudget = 100 * 1024;  // stage obstacle rows only while 2 CTAs/SM still fit
@@ -83,6 +84,7 @@ struct fiss_handle {
   // *_host staging
   DevBuf d_ego, d_end, d_cost, d_flags, d_best_idx, d_best_cost, d_meta, d_records, d_es;  // d_es: in/out block of fiss_eval_end_states_host
   PinBuf h_in, h_out;
+  DevBuf d_arena;  // plan_common latency path: [winners | records | cost | flags]
   std::vector<double> end_cache;
   // product lattice (fiss_grid): device axes [4][kAxisMax] + the expanded [C][4] table in d_end
   DevBuf d_axes;
@@ -439,7 +441,7 @@ int32_t fiss_destroy(fiss_handle* h) {
   cudaSetDevice(h->device);
   for (DevBuf* b : {&h->spline, &h->obs_tab, &h->obs_const, &h->obs_raw, &h->obs_lw, &h->obs_valid, &h->d_ego,
                     &h->d_end, &h->d_cost, &h->d_flags, &h->d_best_idx, &h->d_best_cost, &h->d_meta, &h->d_records,
-                    &h->d_es, &h->d_axes, &h->d_fit_in, &h->d_fit_out})
+                    &h->d_es, &h->d_axes, &h->d_fit_in, &h->d_fit_out, &h->d_arena})
     b->release();
   h->h_in.release();
   h->h_out.release();
@@ -741,6 +743,49 @@ static int32_t plan_common(fiss_handle* h, cudaStream_t st, const double* ego, i
   FISS_CUDA(h, h->d_flags.ensure(total * 4));
   // winners: one device block [best_cost B x 8 | meta B x 8 | best_idx B x 4] so that they travel in ONE copy
   const size_t w_cost = 0, w_meta = (size_t)B * 8, w_idx = (size_t)B * 16, w_bytes = (size_t)B * 20;
+  // Latency path (a few problems): everything the caller asked for is written into ONE device arena
+  // [winners | records | cost | flags] and comes back in ONE copy -- a copy operation costs ~3.6 us of stream time
+  // whatever its size, and a plan cycle of one ego state used to issue four of them.
+  {
+    const size_t a_rec = (w_bytes + 15) & ~(size_t)15, a_vol = a_rec + rec_doubles * 8, a_flags = a_vol + (cost ? total * 8 : 0),
+                 a_end = a_flags + (flags ? total * 4 : 0);
+    if (a_end <= kArenaBytesMax) {
+      FISS_CUDA(h, h->d_arena.ensure(a_end));
+      FISS_CUDA(h, h->h_out.ensure(a_end));
+      FISS_CUDA(h, h->h_in.ensure((size_t)B * 48));
+      char* da = h->d_arena.as<char>();
+      char* ha = h->h_out.as<char>();
+      const void* src = ego;
+      if (!host_is_pinned(ego)) {
+        std::memcpy(h->h_in.p, ego, (size_t)B * 48);
+        src = h->h_in.p;
+      }
+      FISS_CUDA(h, cudaMemcpyAsync(h->d_ego.p, src, (size_t)B * 48, cudaMemcpyHostToDevice, st));
+      const double* ego_p = h->d_ego.as<double>();
+      double* cost_p = cost ? reinterpret_cast<double*>(da + a_vol) : h->d_cost.as<double>();
+      uint32_t* flags_p = flags ? reinterpret_cast<uint32_t*>(da + a_flags) : h->d_flags.as<uint32_t>();
+      if (g) {
+        rc = eval_grid(h, st, ego_p, B, g, n_max, p, cost_p, flags_p, nullptr, n_stride);
+      } else {
+        rc = fiss_eval_candidates_dev(h, stream, ego_p, B, h->d_end.as<double>(), C, p, cost_p, flags_p, nullptr, n_stride);
+      }
+      if (rc != FISS_OK) return rc;
+      rc = fiss_pick_winners_dev(h, stream, ego_p, B, h->d_end.as<double>(), C, p, cost_p, flags_p,
+                                 reinterpret_cast<int32_t*>(da + w_idx), reinterpret_cast<double*>(da + w_cost),
+                                 records ? reinterpret_cast<double*>(da + a_rec) : nullptr,
+                                 reinterpret_cast<int32_t*>(da + w_meta), n_stride);
+      if (rc != FISS_OK) return rc;
+      FISS_CUDA(h, cudaMemcpyAsync(ha, da, a_end, cudaMemcpyDeviceToHost, st));
+      FISS_CUDA(h, cudaStreamSynchronize(st));
+      std::memcpy(best_cost, ha + w_cost, (size_t)B * 8);
+      std::memcpy(best_idx, ha + w_idx, (size_t)B * 4);
+      if (best_meta) std::memcpy(best_meta, ha + w_meta, (size_t)B * 8);
+      if (records) std::memcpy(records, ha + a_rec, rec_doubles * 8);
+      if (cost) std::memcpy(cost, ha + a_vol, total * 8);
+      if (flags) std::memcpy(flags, ha + a_flags, total * 4);
+      return FISS_OK;
+    }
+  }
   FISS_CUDA(h, h->d_best_cost.ensure(w_bytes));
   char* dw = h->d_best_cost.as<char>();
   double* d_bcost = reinterpret_cast<double*>(dw + w_cost);
