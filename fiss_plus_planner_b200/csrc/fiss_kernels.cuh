@@ -124,12 +124,26 @@ __device__ __forceinline__ void pick_scan(const double* __restrict__ pc, const u
                                           int first, int stride, double& bc, int& bi) {
   bc = CUDART_INF;
   bi = -1;
-  for (int i = first; i < C; i += stride) {
-    const double c = pc[i];
-    const bool feasible = (pf[i] & FISS_FLAG_INFEASIBLE_MASK) == 0 && c <= CUDART_INF;  // NaN -> false
-    if (feasible && (bi < 0 || better(c, i, bc, bi))) {
-      bc = c;
-      bi = i;
+  // eight independent loads in flight per thread: the scan is a chain of L2 latencies otherwise (it is on the
+  // latency path of every plan cycle)
+  constexpr int kU = 8;
+  for (int i0 = first; i0 < C; i0 += kU * stride) {
+    double c[kU];
+    uint32_t f[kU];
+#pragma unroll
+    for (int u = 0; u < kU; ++u) {
+      const int i = i0 + u * stride;
+      c[u] = i < C ? pc[i] : CUDART_NAN;
+      f[u] = i < C ? pf[i] : FISS_FLAG_INFEASIBLE_MASK;
+    }
+#pragma unroll
+    for (int u = 0; u < kU; ++u) {
+      const int i = i0 + u * stride;
+      const bool feasible = (f[u] & FISS_FLAG_INFEASIBLE_MASK) == 0 && c[u] <= CUDART_INF;  // NaN -> false
+      if (feasible && (bi < 0 || better(c[u], i, bc, bi))) {
+        bc = c[u];
+        bi = i;
+      }
     }
   }
 }
