@@ -67,7 +67,6 @@ constexpr size_t kArenaBytesMax = 256 * 1024;  // plan_common: results up to thi
 constexpr int kMaxParts = 4;                   // plan_common: pieces a big batch is pipelined in
 constexpr size_t kSmemLimit = 227 * 1024;      // opt-in maximum per CTA on sm_100
 constexpr size_t kSmemObsBudget = 100 * 1024;  // stage obstacle rows only while 2 CTAs/SM still fit
-constexpr size_t kSmemCtaBudget = (228 * 1024) / fiss::kGridMinCtas - 1024;  // lattice kernel: kGridMinCtas CTAs/SM (1 KB/CTA is reserved)
 
 }  // namespace
 
@@ -353,10 +352,14 @@ int32_t eval_grid(fiss_handle* h, cudaStream_t st, const double* d_ego, int B, c
   a.ns_magic = magic(n_stride);
   const int n_groups = (a.d_chunk + fiss::kMatRows - 1) / fiss::kMatRows;
   a.ng_magic = magic(n_groups);
-  // (ego, horizon) pairs per work item: as many as keep kGridMinCtas CTAs per SM resident and every CTA supplied with
-  // a few items (FISS_GRID_SLOTS overrides the upper bound, for A/B runs)
+  // (ego, horizon) pairs per work item: as many as keep the variant's CTAs per SM resident (1 KB of shared memory per
+  // CTA is reserved) and every CTA supplied with a few items (FISS_GRID_SLOTS overrides the upper bound, for A/B runs)
+  const bool yaw = d_mat != nullptr || p->check_curvature;
+  const int min_ctas = fiss::grid_min_ctas(yaw);
+  const size_t kSmemCtaBudget = (228 * 1024) / min_ctas - 1024;
   static const bool slots_forced = std::getenv("FISS_GRID_SLOTS") != nullptr;  // also waives the supply rule (tests)
-  static const int slots_cap = slots_forced ? std::max(1, std::min(fiss::kMaxSlots, std::atoi(std::getenv("FISS_GRID_SLOTS")))) : 2;
+  static const int slots_env = slots_forced ? std::max(1, std::min(fiss::kMaxSlots, std::atoi(std::getenv("FISS_GRID_SLOTS")))) : 0;
+  const int slots_cap = slots_forced ? slots_env : fiss::grid_slots(yaw);
   fiss::GridLayout L{};
   for (a.slots = a.n_chunks > 1 ? 1 : slots_cap;; --a.slots) {
     // the kernel's multiply-shift divisions are exact below 2^20
@@ -366,7 +369,7 @@ int32_t eval_grid(fiss_handle* h, cudaStream_t st, const double* d_ego, int B, c
                        base_items * g->nt < ((int64_t)1 << 32);
     a.E_stage = E_max;
     L = fiss::grid_layout(a.Kp, a.Mp, a.E_stage, a.nv, a.d_chunk, a.n_pad, a.e_pad, a.words, a.slots);
-    const bool supplied = slots_forced || base_items / a.slots >= 2 * (int64_t)fiss::kGridMinCtas * h->sm_count;
+    const bool supplied = slots_forced || base_items / a.slots >= 2 * (int64_t)min_ctas * h->sm_count;
     if (a.slots > 1) {
       if (exact && supplied && L.bytes <= kSmemCtaBudget) break;
       continue;
@@ -379,11 +382,10 @@ int32_t eval_grid(fiss_handle* h, cudaStream_t st, const double* d_ego, int B, c
     break;
   }
   a.items = ((base_items + a.slots - 1) / a.slots) * a.n_chunks;
-  const int warps = std::max(1, std::min(fiss::kGridWarps, a.slots * std::max(g->nv + a.d_chunk, a.d_chunk * g->nv)));
+  const int warps = std::max(1, std::min(fiss::grid_warps(yaw), a.slots * std::max(g->nv + a.d_chunk, a.d_chunk * g->nv)));
   if (L.bytes > kSmemLimit) return fail(h, FISS_ERR_CAPACITY, "lattice row tables exceed 227 KB of shared memory");
   a.lay = L;
   a.row_len = a.slots * a.nv * a.n_pad;
-  const bool yaw = d_mat != nullptr || p->check_curvature;
   return yaw ? launch_grid<true>(h, st, a, L.bytes, warps * 32, 4) : launch_grid<false>(h, st, a, L.bytes, warps * 32, 3);
 }
 

@@ -47,15 +47,24 @@ __device__ long long g_fiss_phase[16];
 
 namespace fiss {
 
+// CTA shape per kernel variant (measured on the B200, cfg4): the winner-only kernel runs best as 8 warps x 3 CTAs per SM
+// with two slots per item; the materialising kernel as 12 warps x 2 CTAs with three slots (its items carry 60-90
+// materialisation tasks, which deal evenly over 12 warps).  Both are register-capped at 80.
 #ifndef FISS_GRID_WARPS
 #define FISS_GRID_WARPS 8
 #endif
-constexpr int kGridWarps = FISS_GRID_WARPS;
-constexpr int kGridThreads = kGridWarps * 32;
 #ifndef FISS_GRID_MIN_CTAS
 #define FISS_GRID_MIN_CTAS 3
 #endif
-constexpr int kGridMinCtas = FISS_GRID_MIN_CTAS;  // resident CTAs per SM the register budget is capped for
+#ifndef FISS_GRID_WARPS_MAT
+#define FISS_GRID_WARPS_MAT 12
+#endif
+#ifndef FISS_GRID_MIN_CTAS_MAT
+#define FISS_GRID_MIN_CTAS_MAT 2
+#endif
+__host__ __device__ constexpr int grid_warps(bool yaw) { return yaw ? FISS_GRID_WARPS_MAT : FISS_GRID_WARPS; }
+__host__ __device__ constexpr int grid_min_ctas(bool yaw) { return yaw ? FISS_GRID_MIN_CTAS_MAT : FISS_GRID_MIN_CTAS; }  // resident CTAs per SM the register budget is capped for
+__host__ __device__ constexpr int grid_slots(bool yaw) { return yaw ? 3 : 2; }  // (ego, horizon) pairs per work item, at most
 constexpr int kAxisMax = 64;  // lattice points per axis
 constexpr int kMaxSlots = 4;  // (ego, horizon) pairs per work item
 #ifndef FISS_MAT_GROUP
@@ -237,7 +246,7 @@ __device__ __forceinline__ void mat_rows(const MatOut& mo, const double2 Pa, con
 
 // kYaw: heading / curvature are needed (materialisation and/or the optional curvature mask).
 template <bool kYaw>
-__global__ void __launch_bounds__(kGridThreads, kGridMinCtas) fiss_grid_kernel(const GridArgs a) {
+__global__ void __launch_bounds__(grid_warps(kYaw) * 32, grid_min_ctas(kYaw)) fiss_grid_kernel(const GridArgs a) {
 #ifdef FISS_PHASE_TIMING
   long long phase_acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   long long phase_t = clock64();

@@ -329,3 +329,19 @@ def test_grid_rejects_bad_grids():
         eng.plan_grid(sc.ego, grid, prm)
     with pytest.raises(FissError, match="1..64"):
         eng.plan_grid(sc.ego, LatticeGrid(np.linspace(-1, 1, 65), [1.0], [4.0], 0.1), prm)
+
+
+@pytest.mark.parametrize("slots", [1, 3])
+def test_grid_kernel_slots_per_item(slots):
+    """The lattice kernel packs several (ego, horizon) pairs into one work item when the batch is large (two by
+    default).  FISS_GRID_SLOTS forces the count for every launch (the library reads it once per process, hence the
+    subprocess): the golden and the lattice-vs-list-kernel parity tests must hold for one and for three pairs too."""
+    import subprocess
+    import sys
+    env = dict(os.environ, FISS_GRID_SLOTS=str(slots))
+    here = os.path.abspath(__file__)
+    res = subprocess.run([sys.executable, "-m", "pytest", "-x", "-q", "-p", "no:cacheprovider",
+                          f"{here}::test_grid_matches_generic_kernel", f"{here}::test_grid_kernel_vs_reference_golden",
+                          f"{here}::test_dense_materialisation_matches_records"],
+                         env=env, capture_output=True, text=True, timeout=600, cwd=os.path.dirname(os.path.dirname(here)))
+    assert res.returncode == 0, res.stdout[-2000:] + res.stderr[-2000:]
