@@ -369,7 +369,11 @@ int32_t eval_grid(fiss_handle* h, cudaStream_t st, const double* d_ego, int B, c
                        base_items * g->nt < ((int64_t)1 << 32);
     a.E_stage = E_max;
     L = fiss::grid_layout(a.Kp, a.Mp, a.E_stage, a.nv, a.d_chunk, a.n_pad, a.e_pad, a.words, a.slots);
-    const bool supplied = slots_forced || base_items / a.slots >= 2 * (int64_t)min_ctas * h->sm_count;
+    // ... and the items must deal evenly over the resident CTAs: the launch lasts ceil(items / CTAs) item times
+    // (640 four-slot items on 296 CTAs: 3 rounds, 72 % busy; 854 three-slot items: 3 rounds, 96 %)
+    const int64_t items_s = (base_items + a.slots - 1) / a.slots, ctas = (int64_t)min_ctas * h->sm_count;
+    const int64_t rounds = (items_s + ctas - 1) / ctas;
+    const bool supplied = slots_forced || (items_s >= 2 * ctas && items_s * 10 >= rounds * ctas * 9);
     if (a.slots > 1) {
       if (exact && supplied && L.bytes <= kSmemCtaBudget) break;
       continue;
