@@ -636,10 +636,12 @@ __global__ void __launch_bounds__(grid_warps(kYaw) * 32, grid_min_ctas(kYaw)) fi
     {
       const uint32_t n_pairs = *npairs;
       const uint32_t n_work = (uint32_t)rows_i * n_pairs;
-      const uint32_t np_magic = n_pairs ? 0xffffffffu / n_pairs + 1u : 0u;  // w / n_pairs == umulhi(w, magic), w < 2^32 / n_pairs
+      // consecutive lanes = consecutive lateral rows of ONE pair: the four 16-byte frame-point reads of a warp are then
+      // broadcasts of ~4 addresses (with the pairs fastest they were 32 scattered ones, ~4-way bank conflicts each)
+      const uint32_t rows_magic = 0xffffffffu / (uint32_t)rows_i + 1u;  // w / rows_i == umulhi(w, magic), w < 2^32 / rows_i
       for (uint32_t wk = threadIdx.x; wk < n_work; wk += blockDim.x) {
-        const int ii = n_pairs == 1u ? (int)wk : (int)__umulhi(wk, np_magic);
-        const uint32_t q = wk - (uint32_t)ii * n_pairs;
+        const uint32_t q = rows_i == 1 ? wk : __umulhi(wk, rows_magic);
+        const int ii = (int)(wk - q * (uint32_t)rows_i);
         const uint32_t pr = pairs[q];
         const int jj = (int)(pr >> 16), e = (int)(pr & 0xffffu);
         const int g = (int)(((uint32_t)jj * nv_magic) >> 20);
