@@ -330,7 +330,7 @@ int32_t eval_grid(fiss_handle* h, cudaStream_t st, const double* d_ego, int B, c
   a.obs_const = h->obs_const.as<double>();
   a.M = h->M; a.Mp = h->Mp; a.mp_shift = h->mp_shift; a.T_obs = h->T_obs; a.final_time_step = h->final_time_step;
   a.words = std::max(1, h->Mp / 32);
-  a.n_pad = (n_max + 2) & ~1;
+  a.n_pad = (n_max + 2) | 1;  // >= n_max + 2 (two NaN pad elements behind a full-length row), odd (bank spread of the row tables)
   a.e_pad = (n_max + p->check_res - 1) / p->check_res;
   a.cost = d_cost; a.flags = d_flags; a.mat = d_mat; a.n_stride = n_stride;
   a.mat_pitch = a.total * n_stride;

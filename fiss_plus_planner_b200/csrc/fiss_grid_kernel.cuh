@@ -78,7 +78,7 @@ constexpr int kMatRows = FISS_MAT_GROUP;  // lateral rows one materialisation ta
 
 // Shared-memory carve-up (byte offsets, 16-byte aligned), used by the host for the launch size too.
 struct GridLayout {
-  uint32_t spline, oc, obs, bbox, bbox_d, axes, slot_d, slot_base, slot_off, lon, lat, lon_cost, lat_cost, dmax, lon_viol,
+  uint32_t spline, oc, obs, bbox, bbox_key, axes, slot_d, slot_base, slot_off, lon, lat, lon_cost, lat_cost, dmax, lon_viol,
       lon_ncart, lon_E, counters, pairs, cflags, masks, listed, near_list, bytes;
 };
 
@@ -101,7 +101,8 @@ struct GridArgs {
   int32_t M, Mp, mp_shift, T_obs, final_time_step;
   int32_t E_stage;     // obstacle rows (centres only) staged in shared memory (0: read them from global / L2)
   int32_t words;       // 32-bit mask words per (row, step) = max(1, Mp/32)
-  int32_t n_pad;       // table row length (>= max n + 1, even)
+  int32_t n_pad;       // table row length (>= max n + 2, odd: rows then start 4 / 2 banks apart, so that reads of one
+                       // column across rows -- the masks, the collision stage -- do not conflict)
   int32_t e_pad;       // mask row length (>= max checked steps)
   double* cost;        // [B*C]
   uint32_t* flags;     // [B*C]
@@ -127,13 +128,13 @@ __host__ __device__ inline GridLayout grid_layout(int Kp, int Mp, int E_stage, i
   L.oc = o;         o += 4u * Mp * 8u;
   L.obs = o;        o += (uint32_t)E_stage * 2u * Mp * 8u;
   L.bbox = o;       o += (uint32_t)e_pad * 4u * 8u;
-  L.bbox_d = o;     o += (uint32_t)e_pad * 4u * 8u;
+  L.bbox_key = o;   o += (uint32_t)e_pad * 4u * 4u;
   L.axes = o;       o += 4u * kAxisMax * 8u;
   L.slot_d = o;     o += 2u * kMaxSlots * 8u * 8u;   // [2][kMaxSlots][8]: ego state (6), T, n -- double-buffered by item parity
   L.slot_base = o;  o += 2u * kMaxSlots * 8u;        // [2][kMaxSlots] id of the slot's candidate (i0, 0, k)
   L.slot_off = o;   o += 2u * kMaxSlots * 4u;        // [2][kMaxSlots] the same relative to slot 0, in output elements
-  L.lon = o;        o += 5u * lon_rows * n_pad * 8u;
-  L.lat = o;        o += lat_rows * n_pad * 8u;
+  L.lon = o;        o += grid_align16(5u * lon_rows * n_pad * 8u);
+  L.lat = o;        o += grid_align16(lat_rows * n_pad * 8u);
   L.lon_cost = o;   o += grid_align16(lon_rows * 8u);
   L.lat_cost = o;   o += grid_align16(lat_rows * 8u);
   L.dmax = o;       o += 16;
@@ -150,14 +151,16 @@ __host__ __device__ inline GridLayout grid_layout(int Kp, int Mp, int E_stage, i
   return L;
 }
 
-// Doubles as unsigned 64-bit keys whose integer order is the numeric order (for shared-memory atomicMin / atomicMax).
-__device__ __forceinline__ unsigned long long order_key(double v) {
-  const long long b = __double_as_longlong(v);
-  return (unsigned long long)(b ^ ((b >> 63) | (long long)0x8000000000000000ull));
+// Floats as unsigned 32-bit keys whose integer order is the numeric order: the per-step bounding boxes are accumulated
+// with NATIVE shared-memory atomicMin / atomicMax (64-bit ones are compare-and-swap loops).  The bounds are rounded
+// outward to float first, so the box only grows: it stays a conservative filter.
+__device__ __forceinline__ uint32_t order_key(float v) {
+  const int32_t b = __float_as_int(v);
+  return (uint32_t)(b ^ ((b >> 31) | (int32_t)0x80000000));
 }
-__device__ __forceinline__ double order_value(unsigned long long k) {
-  const long long b = (long long)k;
-  return __longlong_as_double(b ^ (((b >> 63) ^ -1ll) | (long long)0x8000000000000000ull));
+__device__ __forceinline__ float order_value(uint32_t k) {
+  const int32_t b = (int32_t)k;
+  return __int_as_float(b ^ (((b >> 31) ^ -1) | (int32_t)0x80000000));
 }
 
 // Squared distance, one expression for the box test and the per-row test of stage A' (so that rounding is monotone:
@@ -257,9 +260,10 @@ __global__ void __launch_bounds__(grid_warps(kYaw) * 32, grid_min_ctas(kYaw)) fi
   double* sp = reinterpret_cast<double*>(smem_raw + L.spline);
   double* oc = reinterpret_cast<double*>(smem_raw + L.oc);
   double* obs_s = reinterpret_cast<double*>(smem_raw + L.obs);  // [E_stage][2][Mp]: centres of the checked steps
-  // [e_pad][4]: x_min, x_max, y_min, y_max of the frame points of the rows that check a step, as order-preserving keys
-  unsigned long long* bbox_key = reinterpret_cast<unsigned long long*>(smem_raw + L.bbox);
-  double* bbox = reinterpret_cast<double*>(smem_raw + L.bbox_d);  // the same boxes as doubles (decoded keys)
+  // [e_pad][4]: x_min, x_max, y_min, y_max of the frame points of the rows that check a step: accumulated as float keys
+  // (rounded outward), decoded to doubles once per item
+  double* bbox = reinterpret_cast<double*>(smem_raw + L.bbox);
+  uint32_t* bbox_key = reinterpret_cast<uint32_t*>(smem_raw + L.bbox_key);
   double* ax = reinterpret_cast<double*>(smem_raw + L.axes);
   double* slot_d = reinterpret_cast<double*>(smem_raw + L.slot_d);
   long long* slot_base = reinterpret_cast<long long*>(smem_raw + L.slot_base);
@@ -268,7 +272,7 @@ __global__ void __launch_bounds__(grid_warps(kYaw) * 32, grid_min_ctas(kYaw)) fi
   double* lat = reinterpret_cast<double*>(smem_raw + L.lat);  // [slots * d_chunk][n_pad] lateral offsets d(t)
   double* lon_cost = reinterpret_cast<double*>(smem_raw + L.lon_cost);
   double* lat_cost = reinterpret_cast<double*>(smem_raw + L.lat_cost);
-  unsigned long long* dmax_bits = reinterpret_cast<unsigned long long*>(smem_raw + L.dmax);
+  uint32_t* dmax_bits = reinterpret_cast<uint32_t*>(smem_raw + L.dmax);  // max |d| of the item's lateral rows, a float rounded up
   uint32_t* lon_viol = reinterpret_cast<uint32_t*>(smem_raw + L.lon_viol);
   int32_t* lon_ncart = reinterpret_cast<int32_t*>(smem_raw + L.lon_ncart);
   int32_t* lon_E = reinterpret_cast<int32_t*>(smem_raw + L.lon_E);        // checked steps of the row
@@ -342,18 +346,18 @@ __global__ void __launch_bounds__(grid_warps(kYaw) * 32, grid_min_ctas(kYaw)) fi
   const uint32_t n_chunks = (uint32_t)a.n_chunks, nt = (uint32_t)a.nt;
   const uint32_t n_bk = (uint32_t)a.B * nt;  // (ego, horizon) pairs of the launch
 
-  // Per-item state of stage A' / B: empty boxes (+inf, -inf: infinitely far from everything), clear masks, list marks
-  // and counters.  Runs before the first item and inside stage C of every item (which is the only reader of cflags and
+  // Per-item state of stage A' / B: clear masks, list marks and counters.  Runs before the first item and inside stage C of every item (which is the only reader of cflags and
   // clears them itself), so that an item costs one barrier less.
   auto reset_item_state = [&]() {
     if (threadIdx.x == 0) {
-      *dmax_bits = 0ull;
+      *dmax_bits = 0u;
       *npairs = 0u;
       *n_near = 0u;
       *rows_done = 0u;
       *row_task = 0u;
     }
-    for (int q = threadIdx.x; q < 4 * e_pad; q += blockDim.x) bbox_key[q] = order_key((q & 1) ? -CUDART_INF : CUDART_INF);
+    // empty boxes (+inf, -inf): infinitely far from everything
+    for (int q = threadIdx.x; q < 4 * e_pad; q += blockDim.x) bbox_key[q] = order_key((q & 1) ? -CUDART_INF_F : CUDART_INF_F);
     for (int q = threadIdx.x; q < G * nv * e_pad; q += blockDim.x) listed[q] = 0u;
     for (int q = threadIdx.x; q < G * nv * e_pad * words; q += blockDim.x) masks[q] = 0u;
   };
@@ -495,17 +499,17 @@ __global__ void __launch_bounds__(grid_warps(kYaw) * 32, grid_min_ctas(kYaw)) fi
         // x, y, heading and curvature of the steps outside the Cartesian part come out NaN by propagation
         if (kYaw)
           for (int m = n_cart + lane; m < n_pad; m += 32) P2[base + m] = make_double2(CUDART_NAN, CUDART_NAN);
-        // this row's frame points into the per-step bounding boxes of stage A' (order-preserving integer keys,
-        // shared-memory atomics: min / max commute, so the boxes do not depend on the order the rows arrive in)
+        // this row's frame points into the per-step bounding boxes of stage A' (min / max commute, so the boxes do not
+        // depend on the order the rows arrive in)
         __syncwarp();
         for (int e = lane; e < E_row; e += 32) {
           const double2 fp = P2[base + e * res];
-          atomicMin(&bbox_key[4 * e + 0], order_key(fp.x));
-          atomicMax(&bbox_key[4 * e + 1], order_key(fp.x));
-          atomicMin(&bbox_key[4 * e + 2], order_key(fp.y));
-          atomicMax(&bbox_key[4 * e + 3], order_key(fp.y));
+          atomicMin(&bbox_key[4 * e + 0], order_key(__double2float_rd(fp.x)));
+          atomicMax(&bbox_key[4 * e + 1], order_key(__double2float_ru(fp.x)));
+          atomicMin(&bbox_key[4 * e + 2], order_key(__double2float_rd(fp.y)));
+          atomicMax(&bbox_key[4 * e + 3], order_key(__double2float_ru(fp.y)));
         }
-        // the last row to arrive turns the keys back into doubles, once, for the box test of stage A'
+        // the last row to arrive turns the keys into doubles, once, for the box test of stage A'
         __syncwarp();
         unsigned arrived = 0;
         if (lane == 0) {
@@ -514,7 +518,7 @@ __global__ void __launch_bounds__(grid_warps(kYaw) * 32, grid_min_ctas(kYaw)) fi
         }
         if (__shfl_sync(kFull, arrived, 0) == (unsigned)n_lon - 1u) {
           __threadfence_block();
-          for (int q = lane; q < 4 * e_pad; q += 32) bbox[q] = order_value(bbox_key[q]);
+          for (int q = lane; q < 4 * e_pad; q += 32) bbox[q] = (double)order_value(bbox_key[q]);
         }
       } else {
         // lateral quintic, end (d_end, 0, 0)                        polynomial.py:45-62
@@ -564,7 +568,7 @@ __global__ void __launch_bounds__(grid_warps(kYaw) * 32, grid_min_ctas(kYaw)) fi
         for (int o = 16; o > 0; o >>= 1) dmax = fmax(dmax, __shfl_xor_sync(kFull, dmax, o));
         if (lane == 0) {
           lat_cost[ll] = acc;
-          atomicMax(dmax_bits, (unsigned long long)__double_as_longlong(dmax));  // non-negative doubles order as integers
+          atomicMax(dmax_bits, __float_as_uint(__double2float_ru(dmax)));  // non-negative floats order as integers
         }
       }
     }
@@ -581,7 +585,7 @@ __global__ void __launch_bounds__(grid_warps(kYaw) * 32, grid_min_ctas(kYaw)) fi
     //       (row, step) -- appends it to the work list of stage B.
     if (a.M > 0) {
       mbar_wait(&bar[1], 0);  // obstacle rows landed (phase 0 completes once: later items pass straight through)
-      const double dmax = __longlong_as_double((long long)*dmax_bits);
+      const double dmax = (double)__uint_as_float(*dmax_bits);
       const double reach0 = (dmax + re) * (1.0 + 1.0e-9) + 1.0e-9;
       // lanes = obstacles (their reach is per-lane state), warps stride over the checked steps; with fewer than 32
       // obstacle slots a warp packs 32 / Mp steps per pass
