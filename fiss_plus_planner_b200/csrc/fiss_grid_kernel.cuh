@@ -45,6 +45,14 @@ __device__ long long g_fiss_phase[16];
 #define FISS_PHASE(k) do { } while (0)
 #endif
 
+// Output rows are written once and never read by the kernel: streaming stores (st.global.cs, evict-first) keep them
+// from displacing the tables and the spilled registers in L1 / L2.
+#ifdef FISS_PLAIN_STORES
+#define FISS_ST(ptr, val) (*(ptr) = (val))
+#else
+#define FISS_ST(ptr, val) __stcs((ptr), (val))
+#endif
+
 namespace fiss {
 
 // CTA shape per kernel variant (measured on the B200, cfg4): the winner-only kernel runs best as 8 warps x 3 CTAs per SM
@@ -184,13 +192,11 @@ __device__ __forceinline__ void grid_pos(const double2* __restrict__ P2, const d
 // their fixed FP64 latencies: a warp's issue rate, not its instruction count, bounds this stage.
 struct MatOut {
   double* f_x;       // x field of the item's first candidate (NULL: nothing is written)
-  int64_t pitch;     // elements between two fields
-  double kap_limit;  // optional curvature mask (+inf: off)
   bool has_seg, at_seg, has_kap, writes;
 };
 
 template <int R>
-__device__ __forceinline__ void mat_rows(const MatOut& mo, const double2 Pa, const double2 Ua, const double2 Pb,
+__device__ __forceinline__ void mat_rows(const GridArgs& a, const MatOut& mo, const double2 Pa, const double2 Ua, const double2 Pb,
                                          const double2 Ub, double sd_v, const double* __restrict__ Dr, int n_pad, int off,
                                          int lat_pitch, uint32_t* cf, int nv) {
   double dx[R], dy[R], yaw[R], inv_ds[R], kap[R];
@@ -204,9 +210,9 @@ __device__ __forceinline__ void mat_rows(const MatOut& mo, const double2 Pa, con
     dy[r] = yb - ya;
     if (mo.writes) {  // position and speed leave first: their registers are free for the heading chains
       double* o = mo.f_x + (off + r * lat_pitch);
-      o[0] = mo.at_seg ? xa : xb;
-      o[mo.pitch] = mo.at_seg ? ya : yb;
-      o[3 * mo.pitch] = sd_v;
+      FISS_ST(o, mo.at_seg ? xa : xb);
+      FISS_ST(o + a.mat_pitch, mo.at_seg ? ya : yb);
+      FISS_ST(o + 3 * a.mat_pitch, sd_v);
     }
   }
 #ifdef FISS_EXP_NOMATH
@@ -238,11 +244,11 @@ __device__ __forceinline__ void mat_rows(const MatOut& mo, const double2 Pa, con
 #pragma unroll
   for (int r = 0; r < R; ++r) {
     kap[r] = mo.has_kap ? kap[r] : CUDART_NAN;
-    if (fabs(kap[r]) > mo.kap_limit) atomicOr(cf + r * nv, FISS_FLAG_CURVATURE);
+    if (fabs(kap[r]) > a.kap_limit) atomicOr(cf + r * nv, FISS_FLAG_CURVATURE);
     if (mo.writes) {
       double* o = mo.f_x + (off + r * lat_pitch);
-      o[2 * mo.pitch] = yaw[r];
-      o[4 * mo.pitch] = kap[r];
+      FISS_ST(o + 2 * a.mat_pitch, yaw[r]);
+      FISS_ST(o + 4 * a.mat_pitch, kap[r]);
     }
   }
 }
@@ -709,8 +715,6 @@ __global__ void __launch_bounds__(grid_warps(kYaw) * 32, grid_min_ctas(kYaw)) fi
       // the x field of slot 0's candidate (i0, j = 0, k): uniform per item; the lanes add 32-bit element offsets
       // (the host checks that slots * C * n_stride < 2^31 elements)
       mo.f_x = a.mat ? a.mat + slot_base[par * kMaxSlots] * ns : nullptr;
-      mo.pitch = a.mat_pitch;
-      mo.kap_limit = a.kap_limit;
       const int lat_pitch = a.sd * ns;
       const int lon_pitch = a.sv * ns;
       // tasks t = blk * n_groups + grp.  A task recomputes its lane set-up from t (~35 issue slots against ~400 for its
@@ -753,9 +757,9 @@ __global__ void __launch_bounds__(grid_warps(kYaw) * 32, grid_min_ctas(kYaw)) fi
         const int rows_here = min(kMatRows, rows_i - i_first);  // warp-uniform
         int r = 0;
         for (; r + kMatIlp <= rows_here; r += kMatIlp)
-          mat_rows<kMatIlp>(mo, Pa, Ua, Pb, Ub, sd_v, Dr + r * n_pad, n_pad, off + r * lat_pitch, lat_pitch, cf + r * nv, nv);
+          mat_rows<kMatIlp>(a, mo, Pa, Ua, Pb, Ub, sd_v, Dr + r * n_pad, n_pad, off + r * lat_pitch, lat_pitch, cf + r * nv, nv);
         for (; r < rows_here; ++r)
-          mat_rows<1>(mo, Pa, Ua, Pb, Ub, sd_v, Dr + r * n_pad, n_pad, off + r * lat_pitch, lat_pitch, cf + r * nv, nv);
+          mat_rows<1>(a, mo, Pa, Ua, Pb, Ub, sd_v, Dr + r * n_pad, n_pad, off + r * lat_pitch, lat_pitch, cf + r * nv, nv);
       }
     }
     __syncthreads();
