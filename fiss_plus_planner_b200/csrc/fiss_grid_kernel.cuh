@@ -241,15 +241,24 @@ __device__ __forceinline__ void mat_rows(const GridArgs& a, const MatOut& mo, co
 #pragma unroll
     for (int r = 0; r < R; ++r) kap[r] = (__shfl_down_sync(kFull, yaw[r], 1) - yaw[r]) * inv_ds[r];
   }
+  unsigned over = 0;  // rows whose |curvature| exceeds the optional limit (+inf when the mask is off; NaN never does)
 #pragma unroll
   for (int r = 0; r < R; ++r) {
     kap[r] = mo.has_kap ? kap[r] : CUDART_NAN;
-    if (fabs(kap[r]) > a.kap_limit) atomicOr(cf + r * nv, FISS_FLAG_CURVATURE);
-    if (mo.writes) {
+    over |= fabs(kap[r]) > a.kap_limit ? 1u << r : 0u;
+  }
+  if (mo.writes) {
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
       double* o = mo.f_x + (off + r * lat_pitch);
       FISS_ST(o + 2 * a.mat_pitch, yaw[r]);
       FISS_ST(o + 4 * a.mat_pitch, kap[r]);
     }
+  }
+  if (over) {
+#pragma unroll
+    for (int r = 0; r < R; ++r)
+      if (over >> r & 1u) atomicOr(cf + r * nv, FISS_FLAG_CURVATURE);
   }
 }
 
