@@ -756,7 +756,10 @@ static int32_t plan_common(fiss_handle* h, cudaStream_t st, const double* ego, i
     const size_t a_rec = (w_bytes + 15) & ~(size_t)15, a_vol = a_rec + rec_doubles * 8, a_flags = a_vol + (cost ? total * 8 : 0),
                  a_end = a_flags + (flags ? total * 4 : 0);
     if (a_end <= kArenaBytesMax) {
+      const size_t arena_cap = h->d_arena.cap;
       FISS_CUDA(h, h->d_arena.ensure(a_end));
+      // alignment gaps between the blocks travel with the copy: defined bytes (compute-sanitizer initcheck)
+      if (h->d_arena.cap != arena_cap) FISS_CUDA(h, cudaMemsetAsync(h->d_arena.p, 0, h->d_arena.cap, st));
       FISS_CUDA(h, h->h_out.ensure(a_end));
       FISS_CUDA(h, h->h_in.ensure((size_t)B * 48));
       char* da = h->d_arena.as<char>();
