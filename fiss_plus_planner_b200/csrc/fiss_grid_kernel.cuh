@@ -6,32 +6,35 @@
 // is shared: the longitudinal quartic s(t) -- and with it the reference-line frame (spline segment
 // search, position, unit tangent), the speed / acceleration masks, the truncation length n' and the
 // longitudinal cost terms -- depends on (v_end, T) only; the lateral quintic d(t) and its cost
-// terms depend on (d_end, T) only.  One work item = (ego state b, horizon T_k[, a chunk of lateral
-// rows]); a persistent CTA
+// terms depend on (d_end, T) only.  One work item = `slots` consecutive (ego state b, horizon T_k) pairs
+// [or one pair and a chunk of its lateral rows when the batch is small]; their rows share the stages, the barriers,
+// the per-step bounding boxes and the item bookkeeping -- per-item costs that one 54-candidate pair amortises
+// badly.  A persistent CTA
 //
-//   stage 0  (once per CTA) bulk-TMA the spline table [mbarrier 0] and the checked obstacle rows
+//   stage 0  (once per CTA) bulk-TMA the spline table [mbarrier 0] and the centres of the checked obstacle rows
 //            [mbarrier 1] into shared memory; stage A starts as soon as the spline has landed
-//   stage A  one warp per row, lanes stride over time steps:
-//              longitudinal rows (nv): quartic solve + evaluation, masks, cost terms, frame -> smem
-//                                      tables PX, PY, UX, UY (unit tangent), SD          polynomial.py:5-41
-//              lateral rows (chunk)  : quintic solve + evaluation, cost terms -> smem table D polynomial.py:45-84
+//   stage A  one warp per row (dealt through a shared counter), two time steps per lane in lockstep:
+//              longitudinal rows (slots * nv): quartic solve + evaluation, masks, cost terms, frame -> smem
+//                                      tables P2 = (px, py), U2 = unit tangent, SD          polynomial.py:5-41
+//              lateral rows (slots * rows)   : quintic solve + evaluation, cost terms -> smem table D polynomial.py:45-84
+//            each longitudinal row folds its frame points into per-step bounding boxes (native 32-bit atomics)
 //   stage A' proximity masks: for every (longitudinal row, checked step) a bit per obstacle whose
 //            centre is within (max|d| + r_ego + r_obs) of the FRAME point -- a superset of the
-//            obstacles any candidate on that row can touch at that step (one ballot per pair); the
-//            (row, step) pairs with any bit set are appended to a compact work list
+//            obstacles any candidate on that row can touch at that step; obstacles are first tested against the
+//            step's box, the survivors against the rows; the (row, step) pairs with any bit set are appended to a
+//            compact work list
 //   stage B  collision: one LANE per (lateral row, listed pair): ego pose from the tables, then the exact
 //            predicate (circle reject + closed-set SAT, :168-195) for the listed obstacles only
-//            materialisation (when asked): one warp per candidate (i_d, j_v), lanes stride over time
-//            steps: x = PX - D*UY, y = PY + D*UX, heading / ds / kappa by finite differences
-//            (frenet_optimal_planner.py:121-134), the five output rows streamed to HBM
-//   stage C  one lane per candidate: cost = (lon + lat terms)/n, flags word
+//            materialisation (when asked): lanes = flattened (longitudinal row, step) elements, a task = (block of
+//            31 elements, group of 3 lateral rows): x = PX - D*UY, y = PY + D*UX, heading / ds / kappa by finite
+//            differences (frenet_optimal_planner.py:121-134) with the three rows' FP64 chains in lockstep, the five
+//            output rows streamed to HBM
+//   stage C  one lane per candidate: cost = (lon + lat terms)/n, flags word; reset of the per-item state, fetch of
+//            the next item's ego states
 //
 // so a candidate costs ~2 table reads per step instead of two polynomial solves, a 7-step segment
 // search and an M x n/2 obstacle sweep.  All arithmetic is FP64 with the same expressions as the
 // generic kernel in fiss_kernels.cuh (masks, n' and winners are bit-identical between the two).
-//
-// A work item carries `slots` consecutive (ego, horizon) pairs ("slots"): their rows share the stages, the barriers,
-// the per-step bounding boxes and the item bookkeeping -- per-item costs that one 54-candidate slot amortises badly.
 #pragma once
 
 #include "fiss_kernels.cuh"
