@@ -244,12 +244,8 @@ __device__ __forceinline__ void mat_rows(const GridArgs& a, const MatOut& mo, co
 #pragma unroll
     for (int r = 0; r < R; ++r) kap[r] = (__shfl_down_sync(kFull, yaw[r], 1) - yaw[r]) * inv_ds[r];
   }
-  unsigned over = 0;  // rows whose |curvature| exceeds the optional limit (+inf when the mask is off; NaN never does)
 #pragma unroll
-  for (int r = 0; r < R; ++r) {
-    kap[r] = mo.has_kap ? kap[r] : CUDART_NAN;
-    over |= fabs(kap[r]) > a.kap_limit ? 1u << r : 0u;
-  }
+  for (int r = 0; r < R; ++r) kap[r] = mo.has_kap ? kap[r] : CUDART_NAN;
   if (mo.writes) {
 #pragma unroll
     for (int r = 0; r < R; ++r) {
@@ -258,10 +254,10 @@ __device__ __forceinline__ void mat_rows(const GridArgs& a, const MatOut& mo, co
       FISS_ST(o + 4 * a.mat_pitch, kap[r]);
     }
   }
-  if (over) {
+  if (a.kap_limit < CUDART_INF) {  // the optional curvature mask is on (uniform over the launch; NaN never exceeds)
 #pragma unroll
     for (int r = 0; r < R; ++r)
-      if (over >> r & 1u) atomicOr(cf + r * nv, FISS_FLAG_CURVATURE);
+      if (fabs(kap[r]) > a.kap_limit) atomicOr(cf + r * nv, FISS_FLAG_CURVATURE);
   }
 }
 
