@@ -9,8 +9,9 @@ configs[3] per-GPU shard: 512 ego states per GPU, weak scaling -> 4096 on 8 GPUs
 
 * ``value``   device-resident throughput: ego states already in HBM; the step is the fused lattice
               kernel in FULL-MATERIALISATION mode (x, y, yaw, v, kappa of every candidate written to
-              HBM, FP64: 276 MB per step per GPU, larger than the 126 MB L2) + the pick kernel + the
-              winners' full records.  CUDA events on the launching stream, max over ranks.
+              HBM, FP64: 276 MB per step per GPU, larger than the 126 MB L2) + the record kernel (the pick
+              fused in: argmin per ego state, then the winners' full records).  CUDA events on the launching
+              stream, max over ranks.
 * ``e2e``     the same metric through the host C-ABI call ``fiss_plan_grid_host`` with HOST buffers:
               H2D of the ego states and D2H of winners/records inside the timed region.
 * ``roofline`` the lattice kernel alone: algorithmic bytes (SURVEY 8(d) formula) / its CUDA-event time,
