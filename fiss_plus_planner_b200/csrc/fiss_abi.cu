@@ -83,6 +83,9 @@ struct fiss_handle {
   // *_host staging
   DevBuf d_ego, d_end, d_cost, d_flags, d_best_idx, d_best_cost, d_meta, d_records, d_es;  // d_es: in/out block of fiss_eval_end_states_host
   PinBuf h_in, h_out;
+  // knot index of the installed spline (fiss_set_spline): uniform cells over the knot range, behind the table in h->spline
+  int lut_cells = 0, lut_bytes = 0, lut_iters = 0;
+  double lut_inv_h = 0.0;
   DevBuf d_arena;  // plan_common latency path: [winners | records | cost | flags]
   std::vector<double> end_cache;
   // product lattice (fiss_grid): device axes [4][kAxisMax] + the expanded [C][4] table in d_end
@@ -325,7 +328,11 @@ int32_t eval_grid(fiss_handle* h, cudaStream_t st, const double* d_ego, int B, c
   a.Kp = h->Kp;
   int it = 0;
   while ((1 << it) < std::max(h->K - 1, 1)) ++it;
-  a.search_iters = it;
+  static const bool no_lut = std::getenv("FISS_NO_KNOT_INDEX") != nullptr;  // A/B switch
+  a.lut_cells = no_lut ? 0 : h->lut_cells;
+  a.lut_bytes = no_lut ? 0 : h->lut_bytes;
+  a.lut_inv_h = h->lut_inv_h;
+  a.search_iters = a.lut_cells > 0 ? h->lut_iters : it;
   a.obs_tab = h->obs_tab.as<double>();
   a.obs_const = h->obs_const.as<double>();
   a.M = h->M; a.Mp = h->Mp; a.mp_shift = h->mp_shift; a.T_obs = h->T_obs; a.final_time_step = h->final_time_step;
@@ -368,7 +375,7 @@ int32_t eval_grid(fiss_handle* h, cudaStream_t st, const double* d_ego, int B, c
                        n_blocks * n_groups * n_groups < (1 << 20) && (int64_t)a.slots * a.C * n_stride < ((int64_t)1 << 31) &&
                        base_items * g->nt < ((int64_t)1 << 32);
     a.E_stage = E_max;
-    L = fiss::grid_layout(a.Kp, a.Mp, a.E_stage, a.nv, a.d_chunk, a.n_pad, a.e_pad, a.words, a.slots);
+    L = fiss::grid_layout(a.Kp, a.Mp, a.E_stage, a.nv, a.d_chunk, a.n_pad, a.e_pad, a.words, a.slots, a.lut_bytes);
     // ... and the items must deal evenly over the resident CTAs: the launch lasts ceil(items / CTAs) item times
     // (640 four-slot items on 296 CTAs: 3 rounds, 72 % busy; 854 three-slot items: 3 rounds, 96 %)
     const int64_t items_s = (base_items + a.slots - 1) / a.slots, ctas = (int64_t)min_ctas * h->sm_count;
@@ -381,7 +388,7 @@ int32_t eval_grid(fiss_handle* h, cudaStream_t st, const double* d_ego, int B, c
     if (!exact) return fail(h, FISS_ERR_CAPACITY, "lattice or batch too large for the kernel's index arithmetic (nv * n_stride^2 < 2^20, B * nt^2 < 2^32)");
     if (L.bytes > kSmemCtaBudget) {
       a.E_stage = 0;
-      L = fiss::grid_layout(a.Kp, a.Mp, a.E_stage, a.nv, a.d_chunk, a.n_pad, a.e_pad, a.words, a.slots);
+      L = fiss::grid_layout(a.Kp, a.Mp, a.E_stage, a.nv, a.d_chunk, a.n_pad, a.e_pad, a.words, a.slots, a.lut_bytes);
     }
     break;
   }
@@ -471,15 +478,51 @@ int32_t fiss_set_spline(fiss_handle* h, void* stream, const double* table, int32
   const int Kp = (K + 1) & ~1;  // even row length: every row is a multiple of 16 bytes for the bulk copy
   for (int k = 1; k < K; ++k)
     if (!(table[k] >= table[k - 1])) return fail(h, FISS_ERR_INVALID, "spline knots must be ascending");
-  FISS_CUDA(h, h->h_in.ensure((size_t)9 * Kp * 8));
+  // knot index for the lattice kernel's segment search: kLutCells uniform cells over [knots[0], knots[K-1]),
+  // lut[c] = the largest i with knots[i] <= start of cell c; the kernel brackets an abscissa by the cells around its own
+  // (lut[c-1], lut[c+2] + 1) and bisects `lut_iters` times -- the bound over all cells computed here
+  constexpr int kLutCells = 256;
+  const double s0 = table[0], s1 = table[K - 1];
+  int cells = 0, iters = 0;
+  double inv_h = 0.0;
+  std::vector<int32_t> lut;
+  if (std::isfinite(s0) && std::isfinite(s1) && s1 > s0) {
+    cells = kLutCells;
+    inv_h = cells / (s1 - s0);
+    lut.assign(cells + 1, 0);
+    int i = 0;
+    for (int c = 0; c <= cells; ++c) {
+      const double start = s0 + c * ((s1 - s0) / cells);
+      while (i + 1 < K && table[i + 1] <= start) ++i;
+      lut[c] = i;
+    }
+    int span = 1;
+    for (int c = 0; c < cells; ++c) {
+      const int lo = lut[std::max(c - 1, 0)], hi = std::min(lut[std::min(c + 2, cells)] + 1, K - 1);
+      span = std::max(span, hi - lo);
+    }
+    while ((1 << iters) < span) ++iters;
+    if (!std::isfinite(inv_h)) cells = 0;
+  }
+  const int lut_bytes = cells > 0 ? (int)((((size_t)cells + 1) * 4 + 15) & ~(size_t)15) : 0;
+  const size_t tab_bytes = (size_t)9 * Kp * 8;
+  FISS_CUDA(h, h->h_in.ensure(tab_bytes + lut_bytes));
   double* stage = h->h_in.as<double>();
   for (int r = 0; r < 9; ++r) {
     std::memcpy(stage + (size_t)r * Kp, table + (size_t)r * K, (size_t)K * 8);
     for (int k = K; k < Kp; ++k) stage[(size_t)r * Kp + k] = r == 0 ? INFINITY : 0.0;
   }
-  FISS_CUDA(h, h->spline.ensure((size_t)9 * Kp * 8));
-  FISS_CUDA(h, cudaMemcpyAsync(h->spline.p, stage, (size_t)9 * Kp * 8, cudaMemcpyHostToDevice, st));
+  if (lut_bytes) {
+    std::memset(reinterpret_cast<char*>(stage) + tab_bytes, 0, lut_bytes);
+    std::memcpy(reinterpret_cast<char*>(stage) + tab_bytes, lut.data(), lut.size() * 4);
+  }
+  FISS_CUDA(h, h->spline.ensure(tab_bytes + lut_bytes));
+  FISS_CUDA(h, cudaMemcpyAsync(h->spline.p, stage, tab_bytes + lut_bytes, cudaMemcpyHostToDevice, st));
   FISS_CUDA(h, cudaStreamSynchronize(st));
+  h->lut_cells = cells;
+  h->lut_bytes = lut_bytes;
+  h->lut_iters = iters;
+  h->lut_inv_h = inv_h;
   h->K = K;
   h->Kp = Kp;
   return FISS_OK;
@@ -514,6 +557,8 @@ int32_t fiss_fit_splines_host(fiss_handle* h, void* stream, const double* xy, in
                                  cudaMemcpyDeviceToDevice, st));
     h->K = K;
     h->Kp = Kp;
+    h->lut_cells = h->lut_bytes = h->lut_iters = 0;  // no knot index for a table fitted on the device: full bisection
+    h->lut_inv_h = 0.0;
   }
   if (tables) {
     FISS_CUDA(h, h->h_out.ensure(tab_doubles * 8));

@@ -106,7 +106,10 @@ struct GridArgs {
   int64_t total;       // B * C
   fiss_params p;
   const double* spline;  // [9][Kp]
-  int32_t K, Kp, search_iters;
+  int32_t K, Kp, search_iters;   // search_iters: bisection steps (log2 K, or the bound over the index cells)
+  int32_t lut_cells;        // cells of the knot index behind the spline table (0: none)
+  int32_t lut_bytes;        // its size, a multiple of 16 (it travels in the spline's bulk copy)
+  double lut_inv_h;         // cells / (knots[K-1] - knots[0])
   const double* obs_tab;    // [T_obs][4][Mp]
   const double* obs_const;  // [4][Mp]
   int32_t M, Mp, mp_shift, T_obs, final_time_step;
@@ -131,11 +134,11 @@ struct GridArgs {
 __host__ __device__ inline uint32_t grid_align16(uint32_t v) { return (v + 15u) & ~15u; }
 
 __host__ __device__ inline GridLayout grid_layout(int Kp, int Mp, int E_stage, int nv, int d_chunk, int n_pad, int e_pad,
-                                                  int words, int slots) {
+                                                  int words, int slots, int lut_bytes) {
   GridLayout L;
   const uint32_t lon_rows = (uint32_t)slots * nv, lat_rows = (uint32_t)slots * d_chunk;
   uint32_t o = 16;  // two mbarriers
-  L.spline = o;     o += 9u * Kp * 8u;
+  L.spline = o;     o += 9u * Kp * 8u + (uint32_t)lut_bytes;
   L.oc = o;         o += 4u * Mp * 8u;
   L.obs = o;        o += (uint32_t)E_stage * 2u * Mp * 8u;
   L.bbox = o;       o += (uint32_t)e_pad * 4u * 8u;
@@ -328,7 +331,7 @@ __global__ void __launch_bounds__(grid_warps(kYaw) * 32, grid_min_ctas(kYaw)) fi
   for (int e = 0; e < a.E_stage; ++e)
     if (p.time_step_now + e * p.check_res < a.T_obs) rows_live = e + 1;
   if (threadIdx.x == 0) {
-    const uint32_t spline_bytes = 9u * a.Kp * 8u;
+    const uint32_t spline_bytes = 9u * a.Kp * 8u + (uint32_t)a.lut_bytes;  // the knot index sits behind the table
     mbar_expect_tx(&bar[0], spline_bytes);
     bulk_g2s(sp, a.spline, spline_bytes, &bar[0]);
     mbar_expect_tx(&bar[1], (Mp > 0 ? const_bytes : 0u) + (uint32_t)rows_live * row_bytes);
@@ -476,7 +479,8 @@ __global__ void __launch_bounds__(grid_warps(kYaw) * 32, grid_min_ctas(kYaw)) fi
           if (fabs(sddA) > p.max_accel || (has1 && fabs(sddB) > p.max_accel)) viol |= FISS_FLAG_ACCEL;  // :155
           bool okA, okB;
           double pxA, pyA, txA, tyA, pxB, pyB, txB, tyB;
-          spline_frame2(sp, a.K, a.Kp, a.search_iters, sA, sB, okA, okB, pxA, pyA, txA, tyA, pxB, pyB, txB, tyB);
+          spline_frame2(sp, a.K, a.Kp, a.search_iters, sA, sB, okA, okB, pxA, pyA, txA, tyA, pxB, pyB, txB, tyB,
+                        reinterpret_cast<const int32_t*>(sp + 9 * a.Kp), a.lut_cells, a.lut_inv_h);
           const double rA = rsqrt(txA * txA + tyA * tyA), rB = rsqrt(txB * txB + tyB * tyB);
           if (okA) {
             P2[base + m0] = make_double2(pxA, pyA);

@@ -195,13 +195,32 @@ __device__ __forceinline__ bool spline_frame(const double* __restrict__ sp, int 
 // Two independent abscissae searched and evaluated in lockstep (two dependency chains per lane instead of one; the
 // searches are the latency of the row stage).  Same arithmetic as spline_frame; out-of-range / NaN abscissae still walk
 // the (in-bounds) search and are reported through okA / okB.
+//
+// `lut` (optional, lut_cells > 0): a uniform grid over [knots[0], knots[K-1]), lut[c] = the largest i with knots[i] <= start
+// of cell c (built by fiss_set_spline).  The cell of s, computed in floating point, is off by at most one, so
+// [lut[c-1], lut[c+2] + 1] brackets s like [0, K-1] does, and `iters` (the host's bound over all cells: 1 for evenly spaced
+// knots instead of log2 K) iterations of the same bisection end on the same segment.
+__device__ __forceinline__ void lut_window(const int32_t* __restrict__ lut, int lut_cells, double lut_inv_h, double k0, int K,
+                                           double s, int& lo, int& hi) {
+  int c = (int)((s - k0) * lut_inv_h);  // saturating; NaN -> 0 (such an abscissa is reported through ok)
+  c = max(0, min(c, lut_cells - 1));
+  lo = lut[max(c - 1, 0)];
+  hi = min(lut[min(c + 2, lut_cells)] + 1, K - 1);
+}
+
 __device__ __forceinline__ void spline_frame2(const double* __restrict__ sp, int K, int Kp, int iters, double sA, double sB,
                                               bool& okA, bool& okB, double& pxA, double& pyA, double& txA, double& tyA,
-                                              double& pxB, double& pyB, double& txB, double& tyB) {
+                                              double& pxB, double& pyB, double& txB, double& tyB,
+                                              const int32_t* __restrict__ lut = nullptr, int lut_cells = 0,
+                                              double lut_inv_h = 0.0) {
   const double k0 = sp[0], k1 = sp[K - 1];
   okA = sA >= k0 && sA < k1;
   okB = sB >= k0 && sB < k1;
   int loA = 0, hiA = K - 1, loB = 0, hiB = K - 1;
+  if (lut_cells > 0) {
+    lut_window(lut, lut_cells, lut_inv_h, k0, K, sA, loA, hiA);
+    lut_window(lut, lut_cells, lut_inv_h, k0, K, sB, loB, hiB);
+  }
   for (int it = 0; it < iters; ++it) {
     const int midA = (loA + hiA) >> 1, midB = (loB + hiB) >> 1;
     const bool leA = sp[midA] <= sA, leB = sp[midB] <= sB;
