@@ -573,20 +573,21 @@ __global__ void __launch_bounds__(grid_warps(kYaw) * 32, grid_min_ctas(kYaw)) fi
           const double dddA = 6.0 * la3 + 24.0 * la4 * tA + 60.0 * la5 * tA2;
           const double dddB = 6.0 * la3 + 24.0 * la4 * tB + 60.0 * la5 * tB2;
           acc += p.w_accel * (ddA * ddA) + p.w_jerk * (dddA * dddA) + p.w_offset * (dA * dA);  // cost_function.py:45-47
-          dmax = fmax(dmax, fabs(dA));  // NaN-ignoring: a NaN row has no frame anyway
+          dmax = fabs(dA) > dmax ? fabs(dA) : dmax;  // NaN-ignoring: a NaN row has no frame anyway
           lat[base + m0] = dA;
           if (has1) {
             acc += p.w_accel * (ddB * ddB) + p.w_jerk * (dddB * dddB) + p.w_offset * (dB * dB);
-            dmax = fmax(dmax, fabs(dB));
+            dmax = fabs(dB) > dmax ? fabs(dB) : dmax;
             lat[base + m1] = dB;
           }
         }
         acc = warp_sum(acc);
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) dmax = fmax(dmax, __shfl_xor_sync(kFull, dmax, o));
+        // max |d| of the row as a float rounded up (the reach only grows); non-negative floats order as integers, so the
+        // warp maximum is one integer reduction
+        const uint32_t dmax_row = __reduce_max_sync(kFull, __float_as_uint(__double2float_ru(dmax)));
         if (lane == 0) {
           lat_cost[ll] = acc;
-          atomicMax(dmax_bits, __float_as_uint(__double2float_ru(dmax)));  // non-negative floats order as integers
+          atomicMax(dmax_bits, dmax_row);
         }
       }
     }
