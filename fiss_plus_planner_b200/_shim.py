@@ -81,7 +81,7 @@ def load():
         "fiss_fit_splines_host": (i32, [vp, vp, vp, i32, i32, vp, i32]),
         "fiss_frame_samples_host": (i32, [vp, vp, f64, i32, vp]),
         "fiss_set_obstacles": (i32, [vp, vp, vp, vp, vp, i32, i32, i32]),
-        "fiss_set_obstacles_waymo": (i32, [vp, vp, vp, vp, i32, i32, i32]),
+        "fiss_set_obstacles_waymo": (i32, [vp, vp, vp, vp, i32, i32, i32, C.POINTER(i32)]),
         "fiss_eval_candidates_dev": (i32, [vp, vp, vp, i32, vp, i32, pp, vp, vp, vp, i32]),
         "fiss_eval_grid_dev": (i32, [vp, vp, vp, i32, gp, pp, vp, vp, vp, i32]),
         "fiss_plan_grid_host": (i32, [vp, vp, vp, i32, gp, pp, vp, vp, vp, vp, i32, vp, vp]),

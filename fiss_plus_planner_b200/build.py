@@ -8,8 +8,9 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
 SRC = os.path.join(HERE, "csrc", "fiss_abi.cu")
-HDRS = [os.path.join(HERE, "csrc", "fiss_kernels.cuh"), os.path.join(HERE, "csrc", "fiss_grid_kernel.cuh"),
-        os.path.join(HERE, "csrc", "fiss_math.cuh"), os.path.join(ROOT, "include", "fiss_abi.h")]
+import glob  # noqa: E402
+# every header the translation unit can include: all of csrc/*.cuh + the public ABI header
+HDRS = sorted(glob.glob(os.path.join(HERE, "csrc", "*.cuh"))) + sorted(glob.glob(os.path.join(ROOT, "include", "*.h")))
 OUT = os.path.join(HERE, "libfissgpu.so")
 
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",

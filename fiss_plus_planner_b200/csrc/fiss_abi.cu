@@ -130,6 +130,28 @@ int32_t fail(fiss_handle* h, int32_t code, const std::string& msg) {
       return fail(h, FISS_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(e_));          \
   } while (0)
 
+// Every entry point runs on the handle's device and leaves the caller's current device as it found it (a torch process
+// that plans on cuda:1 must not find its later allocations redirected).
+struct DeviceGuard {
+  int prev = -1, dev;
+  cudaError_t err = cudaSuccess;
+  explicit DeviceGuard(int d) : dev(d) {
+    if (cudaGetDevice(&prev) != cudaSuccess) {
+      cudaGetLastError();
+      prev = -1;
+    }
+    if (prev != dev) err = cudaSetDevice(dev);
+  }
+  ~DeviceGuard() {
+    if (prev >= 0 && prev != dev) cudaSetDevice(prev);
+  }
+  DeviceGuard(const DeviceGuard&) = delete;
+  DeviceGuard& operator=(const DeviceGuard&) = delete;
+};
+#define FISS_ON_DEVICE(h)             \
+  DeviceGuard device_guard_(h->device); \
+  FISS_CUDA(h, device_guard_.err)
+
 // True when `p` is page-locked host memory known to the CUDA runtime (cudaHostAlloc / cudaHostRegister / a torch
 // pinned tensor): the *_host entry points then DMA straight from / into it instead of bouncing through the
 // handle's own pinned staging and a host memcpy.
@@ -394,7 +416,12 @@ int32_t eval_grid(fiss_handle* h, cudaStream_t st, const double* d_ego, int B, c
   }
   a.items = ((base_items + a.slots - 1) / a.slots) * a.n_chunks;
   const int warps = std::max(1, std::min(fiss::grid_warps(yaw), a.slots * std::max(g->nv + a.d_chunk, a.d_chunk * g->nv)));
-  if (L.bytes > kSmemLimit) return fail(h, FISS_ERR_CAPACITY, "lattice row tables exceed 227 KB of shared memory");
+  if (L.bytes > kSmemLimit)
+    return fail(h, FISS_ERR_CAPACITY,
+                "lattice kernel needs " + std::to_string(L.bytes) + " B of shared memory (limit 232448): spline table " +
+                    std::to_string((size_t)9 * a.Kp * 8 + a.lut_bytes) + " B for K = " + std::to_string(a.K) +
+                    " knots (the whole table is staged per CTA: K <= ~3000), row tables " +
+                    std::to_string((size_t)L.lon_cost - L.lon) + " B");
   a.lay = L;
   a.row_len = a.slots * a.nv * a.n_pad;
   return yaw ? launch_grid<true>(h, st, a, L.bytes, warps * 32, 4) : launch_grid<false>(h, st, a, L.bytes, warps * 32, 3);
@@ -405,7 +432,7 @@ int32_t eval_grid(fiss_handle* h, cudaStream_t st, const double* d_ego, int B, c
 // ================================================================================================
 extern "C" {
 
-int32_t fiss_abi_version(void) { return 1; }
+int32_t fiss_abi_version(void) { return 2; }
 
 #ifdef FISS_PHASE_TIMING
 // debug builds only (tools/phase_timing.py): read and reset the per-stage cycle counters of the lattice kernel
@@ -433,7 +460,8 @@ int32_t fiss_create(int32_t device, fiss_handle** out) {
     return fail(nullptr, FISS_ERR_CUDA,
                 std::string("no CUDA device: ") + (e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0"));
   if (device < 0 || device >= count) return fail(nullptr, FISS_ERR_INVALID, "device index out of range");
-  e = cudaSetDevice(device);
+  DeviceGuard device_guard_(device);  // the caller's current device is restored on return
+  e = device_guard_.err;
   if (e != cudaSuccess) return fail(nullptr, FISS_ERR_CUDA, std::string("cudaSetDevice: ") + cudaGetErrorString(e));
   cudaDeviceProp prop;
   e = cudaGetDeviceProperties(&prop, device);
@@ -451,7 +479,7 @@ int32_t fiss_create(int32_t device, fiss_handle** out) {
 
 int32_t fiss_destroy(fiss_handle* h) {
   if (!h) return FISS_OK;
-  cudaSetDevice(h->device);
+  DeviceGuard device_guard_(h->device);
   for (DevBuf* b : {&h->spline, &h->obs_tab, &h->obs_const, &h->obs_raw, &h->obs_lw, &h->obs_valid, &h->d_ego,
                     &h->d_end, &h->d_cost, &h->d_flags, &h->d_best_idx, &h->d_best_cost, &h->d_meta, &h->d_records,
                     &h->d_es, &h->d_axes, &h->d_fit_in, &h->d_fit_out, &h->d_arena})
@@ -474,7 +502,7 @@ int32_t fiss_set_spline(fiss_handle* h, void* stream, const double* table, int32
   if (!h) return FISS_ERR_INVALID;
   if (!table || K < 2) return fail(h, FISS_ERR_INVALID, "spline table needs K >= 2 knots");
   cudaStream_t st = (cudaStream_t)stream;
-  FISS_CUDA(h, cudaSetDevice(h->device));
+  FISS_ON_DEVICE(h);
   const int Kp = (K + 1) & ~1;  // even row length: every row is a multiple of 16 bytes for the bulk copy
   for (int k = 1; k < K; ++k)
     if (!(table[k] >= table[k - 1])) return fail(h, FISS_ERR_INVALID, "spline knots must be ascending");
@@ -534,7 +562,7 @@ int32_t fiss_fit_splines_host(fiss_handle* h, void* stream, const double* xy, in
   if (!xy || L < 1 || K < 2) return fail(h, FISS_ERR_INVALID, "fit_splines: need L >= 1 lanes of K >= 2 way points");
   if (install_lane >= L) return fail(h, FISS_ERR_INVALID, "fit_splines: install_lane out of range");
   cudaStream_t st = (cudaStream_t)stream;
-  FISS_CUDA(h, cudaSetDevice(h->device));
+  FISS_ON_DEVICE(h);
   const int Kp = (K + 1) & ~1;
   const size_t smem = (size_t)6 * Kp * 8;
   if (smem > kSmemLimit) return fail(h, FISS_ERR_CAPACITY, "fit_splines: more way points than 227 KB of shared memory hold");
@@ -577,7 +605,7 @@ int32_t fiss_frame_samples_host(fiss_handle* h, void* stream, double step, int32
   if (!ref || m < 1 || !(step > 0.0)) return fail(h, FISS_ERR_INVALID, "frame_samples: bad arguments");
   if (h->K < 2) return fail(h, FISS_ERR_STATE, "no reference line: call fiss_set_spline / fiss_fit_splines_host first");
   cudaStream_t st = (cudaStream_t)stream;
-  FISS_CUDA(h, cudaSetDevice(h->device));
+  FISS_ON_DEVICE(h);
   const size_t bytes = (size_t)m * 4 * 8;
   FISS_CUDA(h, h->d_fit_out.ensure(bytes));
   FISS_CUDA(h, h->h_out.ensure(bytes));
@@ -617,7 +645,7 @@ int32_t fiss_set_obstacles(fiss_handle* h, void* stream, const double* xyth, con
                            int32_t M, int32_t T_obs, int32_t final_time_step) {
   if (!h) return FISS_ERR_INVALID;
   cudaStream_t st = (cudaStream_t)stream;
-  FISS_CUDA(h, cudaSetDevice(h->device));
+  FISS_ON_DEVICE(h);
   if (M > 0 && (!xyth || !lw || !valid || T_obs < 1))
     return fail(h, FISS_ERR_INVALID, "obstacle arrays are NULL or T_obs < 1");
   int32_t rc = obstacle_dims(h, M, T_obs, final_time_step);
@@ -642,27 +670,47 @@ int32_t fiss_set_obstacles(fiss_handle* h, void* stream, const double* xyth, con
 }
 
 int32_t fiss_set_obstacles_waymo(fiss_handle* h, void* stream, const float* trajs, const uint8_t* mask, int32_t N,
-                                 int32_t T, int32_t final_time_step) {
+                                 int32_t T, int32_t final_time_step, int32_t* n_kept) {
   if (!h) return FISS_ERR_INVALID;
   cudaStream_t st = (cudaStream_t)stream;
-  FISS_CUDA(h, cudaSetDevice(h->device));
+  FISS_ON_DEVICE(h);
+  if (N < 0 || T < 0) return fail(h, FISS_ERR_INVALID, "negative waymo array size");
   if (N > 0 && (!trajs || !mask || T < 1)) return fail(h, FISS_ERR_INVALID, "waymo arrays are NULL or T < 1");
-  int32_t rc = obstacle_dims(h, N, T, final_time_step);
-  if (rc != FISS_OK || N == 0) return rc;
+  // convert_waymo_obstacle_to_cr (waymo_interface.py:24-76): the trajectory of agent i is steps 1.. up to the first masked
+  // step (:45-54); an agent whose trajectory comes out empty is NOT appended (:58) -- it has no state at any step, the
+  // initial one included, and the agents behind it move up (obstacles[0], hence final_time_step, is the first KEPT agent)
+  std::vector<int32_t> keep_end;  // [kept agent ids | last step with a state]
+  std::vector<int32_t> t_end;
+  for (int i = 0; i < N; ++i) {
+    const uint8_t* mi = mask + (size_t)i * T;
+    if (T < 2 || !mi[1]) continue;
+    int te = 1;
+    while (te + 1 < T && mi[te + 1]) ++te;
+    keep_end.push_back(i);
+    t_end.push_back(te);
+  }
+  const int32_t M = (int32_t)keep_end.size();
+  if (n_kept) *n_kept = M;
+  // obstacles[0].prediction.final_time_step = the last state of the first kept agent's trajectory
+  // (frenet_optimal_planner.py:173); an explicit value >= 0 overrides it
+  const int32_t fts = final_time_step >= 0 ? final_time_step : (M > 0 ? t_end[0] : 0);
+  int32_t rc = obstacle_dims(h, M, T, fts);
+  if (rc != FISS_OK || M == 0) return rc;
+  keep_end.insert(keep_end.end(), t_end.begin(), t_end.end());
   const size_t n_state = (size_t)N * T;
   FISS_CUDA(h, h->obs_raw.ensure(n_state * 11 * 4));
-  FISS_CUDA(h, h->obs_valid.ensure(n_state));
+  FISS_CUDA(h, h->obs_valid.ensure((size_t)2 * M * 4));
   FISS_CUDA(h, h->obs_tab.ensure((size_t)T * h->Mp * 32));
   FISS_CUDA(h, h->obs_const.ensure((size_t)h->Mp * 32));
   FISS_CUDA(h, cudaMemcpyAsync(h->obs_raw.p, trajs, n_state * 11 * 4, cudaMemcpyHostToDevice, st));
-  FISS_CUDA(h, cudaMemcpyAsync(h->obs_valid.p, mask, n_state, cudaMemcpyHostToDevice, st));
+  FISS_CUDA(h, cudaMemcpyAsync(h->obs_valid.p, keep_end.data(), (size_t)2 * M * 4, cudaMemcpyHostToDevice, st));
   const int64_t work = std::max<int64_t>((int64_t)T * h->Mp, h->Mp);
   fiss::fiss_obstacle_prep_waymo_kernel<<<(unsigned)((work + 255) / 256), 256, 0, st>>>(
-      h->obs_raw.as<float>(), h->obs_valid.as<uint8_t>(), N, h->Mp, T, h->obs_tab.as<double>(),
-      h->obs_const.as<double>());
+      h->obs_raw.as<float>(), h->obs_valid.as<int32_t>(), h->obs_valid.as<int32_t>() + M, M, h->Mp, T,
+      h->obs_tab.as<double>(), h->obs_const.as<double>());
   h->launches++;
   FISS_CUDA(h, cudaGetLastError());
-  FISS_CUDA(h, cudaStreamSynchronize(st));
+  FISS_CUDA(h, cudaStreamSynchronize(st));  // keep_end (and the caller's arrays) may go away on return
   return FISS_OK;
 }
 
@@ -674,7 +722,7 @@ int32_t fiss_eval_candidates_dev(fiss_handle* h, void* stream, const double* d_e
   if (!d_ego || !d_end || B < 1 || C < 1) return fail(h, FISS_ERR_INVALID, "ego/end pointers or sizes invalid");
   int32_t rc = check_params(h, p);
   if (rc != FISS_OK) return rc;
-  FISS_CUDA(h, cudaSetDevice(h->device));
+  FISS_ON_DEVICE(h);
   LaunchPlan lp{};
   rc = plan_launch(h, p, (int64_t)B * C, n_stride, lp);
   if (rc != FISS_OK) return rc;
@@ -700,7 +748,7 @@ int32_t fiss_full_records_dev(fiss_handle* h, void* stream, const double* d_ego6
   if (!d_ego6 || !d_end || !d_records || N < 1) return fail(h, FISS_ERR_INVALID, "full_records: bad arguments");
   int32_t rc = check_params(h, p);
   if (rc != FISS_OK) return rc;
-  FISS_CUDA(h, cudaSetDevice(h->device));
+  FISS_ON_DEVICE(h);
   LaunchPlan lp{};
   rc = plan_launch(h, p, N, n_stride, lp);
   if (rc != FISS_OK) return rc;
@@ -727,7 +775,7 @@ int32_t fiss_pick_winners_dev(fiss_handle* h, void* stream, const double* d_ego,
     return fail(h, FISS_ERR_INVALID, "pick_winners: bad arguments");
   int32_t rc = check_params(h, p);
   if (rc != FISS_OK) return rc;
-  FISS_CUDA(h, cudaSetDevice(h->device));
+  FISS_ON_DEVICE(h);
   cudaStream_t st = (cudaStream_t)stream;
   if (!d_records) {
     fiss::fiss_pick_kernel<<<B, fiss::kPickThreads, 0, st>>>(d_cost, d_flags, C, d_best_idx, d_best_cost, d_end, d_best_meta);
@@ -874,6 +922,20 @@ static int32_t plan_common(fiss_handle* h, cudaStream_t st, const double* ego, i
     FISS_CUDA(h, cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
     for (auto& ev : h->part_done) FISS_CUDA(h, cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
   }
+  // A failure after the first piece was issued must not return while copies into the caller's buffers are in flight
+  // (the caller may free them, and the next call may reallocate the device buffers under the running copy).
+  const auto drain = [&]() {
+    cudaStreamSynchronize(st);
+    if (h->copy_stream) cudaStreamSynchronize(h->copy_stream);
+  };
+#define FISS_CUDA_DRAIN(expr)                                                                  \
+  do {                                                                                         \
+    cudaError_t e_ = (expr);                                                                   \
+    if (e_ != cudaSuccess) {                                                                   \
+      drain();                                                                                 \
+      return fail(h, FISS_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(e_));       \
+    }                                                                                          \
+  } while (0)
   for (int part = 0; part < n_parts; ++part) {
     const int b0 = (int)((int64_t)B * part / n_parts), bn = (int)((int64_t)B * (part + 1) / n_parts) - b0;
     const double* ego_p = h->d_ego.as<double>() + (size_t)b0 * 6;
@@ -884,28 +946,35 @@ static int32_t plan_common(fiss_handle* h, cudaStream_t st, const double* ego, i
     } else {
       rc = fiss_eval_candidates_dev(h, stream, ego_p, bn, h->d_end.as<double>(), C, p, cost_p, flags_p, nullptr, n_stride);
     }
-    if (rc != FISS_OK) return rc;
+    if (rc != FISS_OK) {
+      drain();
+      return rc;
+    }
     const size_t rec_off = (size_t)b0 * FISS_REC_ROWS * n_stride, rec_len = (size_t)bn * FISS_REC_ROWS * n_stride;
     rc = fiss_pick_winners_dev(h, stream, ego_p, bn, h->d_end.as<double>(), C, p, cost_p, flags_p, d_bidx + b0, d_bcost + b0,
                                records ? h->d_records.as<double>() + rec_off : nullptr, d_bmeta + 2 * (size_t)b0, n_stride);
-    if (rc != FISS_OK) return rc;
+    if (rc != FISS_OK) {
+      drain();
+      return rc;
+    }
     cudaStream_t cs = st;
     if (n_parts > 1) {
-      FISS_CUDA(h, cudaEventRecord(h->part_done[part], st));
-      FISS_CUDA(h, cudaStreamWaitEvent(h->copy_stream, h->part_done[part], 0));
+      FISS_CUDA_DRAIN(cudaEventRecord(h->part_done[part], st));
+      FISS_CUDA_DRAIN(cudaStreamWaitEvent(h->copy_stream, h->part_done[part], 0));
       cs = h->copy_stream;
     }
     if (records)
-      FISS_CUDA(h, cudaMemcpyAsync((double*)t_rec + rec_off, h->d_records.as<double>() + rec_off, rec_len * 8,
-                                   cudaMemcpyDeviceToHost, cs));
+      FISS_CUDA_DRAIN(cudaMemcpyAsync((double*)t_rec + rec_off, h->d_records.as<double>() + rec_off, rec_len * 8,
+                                      cudaMemcpyDeviceToHost, cs));
     if (cost)
-      FISS_CUDA(h, cudaMemcpyAsync((double*)t_vol + (size_t)b0 * C, cost_p, (size_t)bn * C * 8, cudaMemcpyDeviceToHost, cs));
+      FISS_CUDA_DRAIN(cudaMemcpyAsync((double*)t_vol + (size_t)b0 * C, cost_p, (size_t)bn * C * 8, cudaMemcpyDeviceToHost, cs));
     if (flags)
-      FISS_CUDA(h, cudaMemcpyAsync((uint32_t*)t_flags + (size_t)b0 * C, flags_p, (size_t)bn * C * 4, cudaMemcpyDeviceToHost, cs));
+      FISS_CUDA_DRAIN(cudaMemcpyAsync((uint32_t*)t_flags + (size_t)b0 * C, flags_p, (size_t)bn * C * 4, cudaMemcpyDeviceToHost, cs));
   }
-  FISS_CUDA(h, cudaMemcpyAsync(ho + o_win, dw, w_bytes, cudaMemcpyDeviceToHost, st));
-  FISS_CUDA(h, cudaStreamSynchronize(st));
-  if (n_parts > 1) FISS_CUDA(h, cudaStreamSynchronize(h->copy_stream));
+  FISS_CUDA_DRAIN(cudaMemcpyAsync(ho + o_win, dw, w_bytes, cudaMemcpyDeviceToHost, st));
+  FISS_CUDA_DRAIN(cudaStreamSynchronize(st));
+  if (n_parts > 1) FISS_CUDA_DRAIN(cudaStreamSynchronize(h->copy_stream));
+#undef FISS_CUDA_DRAIN
   std::memcpy(best_cost, ho + o_win + w_cost, (size_t)B * 8);
   std::memcpy(best_idx, ho + o_win + w_idx, (size_t)B * 4);
   if (best_meta) std::memcpy(best_meta, ho + o_win + w_meta, (size_t)B * 8);
@@ -925,7 +994,7 @@ int32_t fiss_plan_lattice_host(fiss_handle* h, void* stream, const double* ego, 
   if (rc != FISS_OK) return rc;
   rc = check_end_states(h, end, C, n_stride);
   if (rc != FISS_OK) return rc;
-  FISS_CUDA(h, cudaSetDevice(h->device));
+  FISS_ON_DEVICE(h);
   cudaStream_t st = (cudaStream_t)stream;
   rc = upload_end_states(h, st, end, C);
   if (rc != FISS_OK) return rc;
@@ -938,7 +1007,7 @@ int32_t fiss_eval_grid_dev(fiss_handle* h, void* stream, const double* d_ego, in
   if (!d_ego || !d_cost || !d_flags || B < 1) return fail(h, FISS_ERR_INVALID, "eval_grid: bad arguments");
   int32_t rc = check_params(h, p);
   if (rc != FISS_OK) return rc;
-  FISS_CUDA(h, cudaSetDevice(h->device));
+  FISS_ON_DEVICE(h);
   int n_max = 0;
   rc = ensure_grid(h, (cudaStream_t)stream, g, p, &n_max);
   if (rc != FISS_OK) return rc;
@@ -952,7 +1021,7 @@ int32_t fiss_plan_grid_host(fiss_handle* h, void* stream, const double* ego, int
   if (!ego || !best_idx || !best_cost || B < 1) return fail(h, FISS_ERR_INVALID, "plan_grid: bad arguments");
   int32_t rc = check_params(h, p);
   if (rc != FISS_OK) return rc;
-  FISS_CUDA(h, cudaSetDevice(h->device));
+  FISS_ON_DEVICE(h);
   cudaStream_t st = (cudaStream_t)stream;
   int n_max = 0;
   rc = ensure_grid(h, st, g, p, &n_max);
@@ -971,7 +1040,7 @@ int32_t fiss_eval_end_states_host(fiss_handle* h, void* stream, const double* eg
   if (rc != FISS_OK) return rc;
   rc = check_end_states(h, end, N, n_stride);
   if (rc != FISS_OK) return rc;
-  FISS_CUDA(h, cudaSetDevice(h->device));
+  FISS_ON_DEVICE(h);
   cudaStream_t st = (cudaStream_t)stream;
   const size_t rec_doubles = records ? (size_t)N * FISS_REC_ROWS * n_stride : 0;
   // one block in ([ego 48 B | end N x 32 B]) and one block out ([cost N x 8 | flags N x 4]): this call sits on the

@@ -77,6 +77,12 @@ __host__ __device__ constexpr int grid_warps(bool yaw) { return yaw ? FISS_GRID_
 __host__ __device__ constexpr int grid_min_ctas(bool yaw) { return yaw ? FISS_GRID_MIN_CTAS_MAT : FISS_GRID_MIN_CTAS; }  // resident CTAs per SM the register budget is capped for
 __host__ __device__ constexpr int grid_slots(bool yaw) { return yaw ? 3 : 2; }  // (ego, horizon) pairs per work item, at most
 constexpr int kAxisMax = 64;  // lattice points per axis
+// components of an obstacle row staged in shared memory: 2 = centres only (cos / sin of the few exact tests come from
+// L2), 4 = the whole row (the exact predicate then never leaves the SM)
+#ifndef FISS_OBS_COMP
+#define FISS_OBS_COMP 2
+#endif
+constexpr int kObsComp = FISS_OBS_COMP;
 constexpr int kMaxSlots = 4;  // (ego, horizon) pairs per work item
 #ifndef FISS_MAT_GROUP
 #define FISS_MAT_GROUP 3
@@ -140,7 +146,7 @@ __host__ __device__ inline GridLayout grid_layout(int Kp, int Mp, int E_stage, i
   uint32_t o = 16;  // two mbarriers
   L.spline = o;     o += 9u * Kp * 8u + (uint32_t)lut_bytes;
   L.oc = o;         o += 4u * Mp * 8u;
-  L.obs = o;        o += (uint32_t)E_stage * 2u * Mp * 8u;
+  L.obs = o;        o += (uint32_t)E_stage * (uint32_t)kObsComp * Mp * 8u;
   L.bbox = o;       o += (uint32_t)e_pad * 4u * 8u;
   L.bbox_key = o;   o += (uint32_t)e_pad * 4u * 4u;
   L.axes = o;       o += 4u * kAxisMax * 8u;
@@ -326,7 +332,7 @@ __global__ void __launch_bounds__(grid_warps(kYaw) * 32, grid_min_ctas(kYaw)) fi
   }
   __syncthreads();
   const uint32_t const_bytes = 4u * Mp * 8u;
-  const uint32_t row_bytes = 2u * Mp * 8u;  // cx, cy of one step: the first two components of a table row
+  const uint32_t row_bytes = (uint32_t)kObsComp * Mp * 8u;  // cx, cy (and cos, sin) of one step: the leading components of a table row
   int rows_live = 0;  // staged rows that exist in the table (time < T_obs)
   for (int e = 0; e < a.E_stage; ++e)
     if (p.time_step_now + e * p.check_res < a.T_obs) rows_live = e + 1;
@@ -337,20 +343,22 @@ __global__ void __launch_bounds__(grid_warps(kYaw) * 32, grid_min_ctas(kYaw)) fi
     mbar_expect_tx(&bar[1], (Mp > 0 ? const_bytes : 0u) + (uint32_t)rows_live * row_bytes);
     if (Mp > 0) bulk_g2s(oc, a.obs_const, const_bytes, &bar[1]);
     for (int e = 0; e < rows_live; ++e)
-      bulk_g2s(obs_s + (int64_t)e * 2 * Mp, a.obs_tab + (int64_t)(p.time_step_now + e * p.check_res) * 4 * Mp,
+      bulk_g2s(obs_s + (int64_t)e * kObsComp * Mp, a.obs_tab + (int64_t)(p.time_step_now + e * p.check_res) * 4 * Mp,
                row_bytes, &bar[1]);
   }
   // staged rows past the end of the predictions: nobody has a state there (state_at_time -> None)
-  for (int64_t q = (int64_t)rows_live * 2 * Mp + threadIdx.x; q < (int64_t)a.E_stage * 2 * Mp; q += blockDim.x)
+  for (int64_t q = (int64_t)rows_live * kObsComp * Mp + threadIdx.x; q < (int64_t)a.E_stage * kObsComp * Mp; q += blockDim.x)
     obs_s[q] = kObsFar;
   for (int q = threadIdx.x; q < 4 * kAxisMax; q += blockDim.x) ax[q] = a.axes[q];
 
   // centres (cx, cy) of checked step e: staged rows, or the global table
   const double* obs = a.E_stage > 0 ? obs_s : a.obs_tab + (int64_t)p.time_step_now * 4 * Mp;
-  const int obs_pitch = a.E_stage > 0 ? 2 * Mp : p.check_res * 4 * Mp;
-  // (cos, sin) of the obstacles at checked step e: always the global table (only the exact predicate reads them)
-  const double* obs_cs = a.obs_tab + (int64_t)p.time_step_now * 4 * Mp + 2 * Mp;
-  const int cs_pitch = p.check_res * 4 * Mp;
+  const int obs_pitch = a.E_stage > 0 ? kObsComp * Mp : p.check_res * 4 * Mp;
+  // (cos, sin) of the obstacles at checked step e (only the exact predicate reads them): staged with the centres
+  // (kObsComp == 4) or the global table
+  const bool cs_staged = kObsComp == 4 && a.E_stage > 0;
+  const double* obs_cs = cs_staged ? obs_s + 2 * Mp : a.obs_tab + (int64_t)p.time_step_now * 4 * Mp + 2 * Mp;
+  const int cs_pitch = cs_staged ? 4 * Mp : p.check_res * 4 * Mp;
   const double hle = 0.5 * p.ego_length, hwe = 0.5 * p.ego_width;
   const double re = sqrt(hle * hle + hwe * hwe);
 
@@ -427,6 +435,11 @@ __global__ void __launch_bounds__(grid_warps(kYaw) * 32, grid_min_ctas(kYaw)) fi
     __syncthreads();
     // last item of this CTA: a dependent launch (the record kernel, fiss_pick_winners_dev) may start staging its tables
     if (item + gridDim.x >= n_items) pdl_launch_dependents();
+#ifdef FISS_EARLY_SLOTS
+    // the next item's slots: the other buffer is free from here on, and the global loads complete under stage A (issued
+    // at the end of stage C, their latency was exposed at this barrier)
+    load_slots(item + gridDim.x, par ^ 1);
+#endif
     FISS_PHASE(1);
 
     // ---- stage A: one warp per row, rows dealt dynamically (the longitudinal rows, ~3x the work of a lateral row,
@@ -802,7 +815,9 @@ __global__ void __launch_bounds__(grid_warps(kYaw) * 32, grid_min_ctas(kYaw)) fi
         a.flags[out_id] = viol | extra | ((uint32_t)n_cart << FISS_FLAG_NCART_SHIFT);
       }
       reset_item_state();
+#ifndef FISS_EARLY_SLOTS
       load_slots(item + gridDim.x, par ^ 1);
+#endif
     }
   }
 #ifdef FISS_PHASE_TIMING

@@ -700,31 +700,31 @@ __global__ void fiss_obstacle_prep_kernel(const double* __restrict__ xyth, const
   obstacle_store(tab, oc, Mp, T, q, present, x, y, th, l, w);
 }
 
-// Waymo wire format (waymo_interface.py:24-76): float32 [N][T][11] + mask [N][T] -> the same rows.
-// valid(t) = all mask[1..t] set (the conversion `break`s at the first masked step, :49-52); step 0 is the
-// initial state and always present; length/width from step 0 (:33-34).
-__global__ void fiss_obstacle_prep_waymo_kernel(const float* __restrict__ trajs, const uint8_t* __restrict__ mask,
-                                                int N, int Mp, int T, double* __restrict__ tab,
-                                                double* __restrict__ oc) {
+// Waymo wire format (waymo_interface.py:24-76): float32 [N][T][11] = (x, y, z, l, w, h, heading, vx, vy, valid, type).
+// The host has already applied the conversion's keep / cut rules (fiss_set_obstacles_waymo): table column j is agent
+// keep[j], which has a state at steps 0..t_end[j] -- step 0 is the initial state, never masked (:36-40) -- and none
+// behind (state_at_time -> None); length / width from step 0 (:33-34).  float32 values widen to double exactly, as they
+// do when the reference hands them to shapely.
+__global__ void fiss_obstacle_prep_waymo_kernel(const float* __restrict__ trajs, const int32_t* __restrict__ keep,
+                                                const int32_t* __restrict__ t_end, int M, int Mp, int T,
+                                                double* __restrict__ tab, double* __restrict__ oc) {
   const int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const int jc = (int)(q < Mp ? q : 0);
-  const double l = (q < Mp && jc < N) ? (double)trajs[((int64_t)jc * T) * 11 + 3] : 0.0;
-  const double w = (q < Mp && jc < N) ? (double)trajs[((int64_t)jc * T) * 11 + 4] : 0.0;
+  const bool has_c = q < Mp && jc < M;
+  const int64_t agent_c = has_c ? keep[jc] : 0;
+  const double l = has_c ? (double)trajs[(agent_c * T) * 11 + 3] : 0.0;
+  const double w = has_c ? (double)trajs[(agent_c * T) * 11 + 4] : 0.0;
   bool present = false;
   double x = 0.0, y = 0.0, th = 0.0;
   if (q < (int64_t)T * Mp) {
     const int t = (int)(q / Mp);
     const int j = (int)(q - (int64_t)t * Mp);
-    if (j < N) {
-      bool ok = true;
-      for (int u = 1; u <= t; ++u) ok = ok && mask[(int64_t)j * T + u] != 0;
-      if (ok) {
-        const float* s = trajs + ((int64_t)j * T + t) * 11;
-        present = true;
-        x = (double)s[0];
-        y = (double)s[1];
-        th = (double)s[6];
-      }
+    if (j < M && t <= t_end[j]) {
+      const float* s = trajs + ((int64_t)keep[j] * T + t) * 11;
+      present = true;
+      x = (double)s[0];
+      y = (double)s[1];
+      th = (double)s[6];
     }
   }
   obstacle_store(tab, oc, Mp, T, q, present, x, y, th, l, w);

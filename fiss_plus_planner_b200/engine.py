@@ -138,7 +138,10 @@ class FissEngine:
             raise FissError(f"fiss_create failed ({rc}): {self._lib.fiss_last_error(None).decode()}")
         self.device = int(device)
         self.num_obstacles = 0
-        self._obstacle_token = None
+        # scene versions: bumped whenever the installed reference line / obstacle table changes, so that several planners
+        # (or a planner and its lazy candidate bundles) sharing one engine can tell that the tables are no longer theirs
+        self.spline_token = 0
+        self.obstacle_token = 0
 
     # ------------------------------------------------------------------ plumbing
     def close(self):
@@ -170,6 +173,7 @@ class FissEngine:
         assert table.ndim == 2 and table.shape[0] == 9, "spline table must be [9, K]"
         self._check(self._lib.fiss_set_spline(self._h, self._stream(stream), _shim.ptr(table), table.shape[1]),
                     "fiss_set_spline")
+        self.spline_token += 1
 
     def fit_splines(self, lanes, install: int = 0, stream=None) -> np.ndarray:
         """Natural cubic splines of ``lanes [L, K, 2]`` (or one lane ``[K, 2]``) fitted on the device (Thomas
@@ -183,6 +187,8 @@ class FissEngine:
         tables = np.empty((n_lanes, 9, k), np.float64)
         self._check(self._lib.fiss_fit_splines_host(self._h, self._stream(stream), _shim.ptr(lanes), n_lanes, k,
                                                     _shim.ptr(tables), int(install)), "fiss_fit_splines_host")
+        if install >= 0:
+            self.spline_token += 1
         return tables
 
     def frame_samples(self, s_end: float, step: float = 0.1, stream=None) -> np.ndarray:
@@ -199,6 +205,7 @@ class FissEngine:
             self._check(self._lib.fiss_set_obstacles(self._h, self._stream(stream), None, None, None, 0, 0,
                                                      int(final_time_step)), "fiss_set_obstacles")
             self.num_obstacles = 0
+            self.obstacle_token += 1
             return
         xyth = np.ascontiguousarray(xyth, dtype=np.float64)
         lw = np.ascontiguousarray(lw, dtype=np.float64)
@@ -208,15 +215,22 @@ class FissEngine:
         self._check(self._lib.fiss_set_obstacles(self._h, self._stream(stream), _shim.ptr(xyth), _shim.ptr(lw),
                                                  _shim.ptr(valid), m, t, int(final_time_step)), "fiss_set_obstacles")
         self.num_obstacles = m
+        self.obstacle_token += 1
 
-    def set_obstacles_waymo(self, trajs, mask, final_time_step: int, stream=None):
+    def set_obstacles_waymo(self, trajs, mask, final_time_step: int = -1, stream=None) -> int:
+        """Obstacle table straight from the Waymo wire format (``trajs [N, T, 11]`` float32, ``mask [N, T]``) with the
+        keep / cut rules of ``convert_waymo_obstacle_to_cr`` (waymo_interface.py:24-76): returns the number of agents
+        kept as obstacles.  ``final_time_step < 0`` takes it from the first kept agent, like the reference's list."""
         trajs = np.ascontiguousarray(trajs, dtype=np.float32)
-        mask = np.ascontiguousarray(mask, dtype=np.uint8)
+        mask = np.ascontiguousarray(np.asarray(mask) != 0, dtype=np.uint8)
         n, t, f = trajs.shape
         assert f == 11 and mask.shape == (n, t)
+        kept = C.c_int32(0)
         self._check(self._lib.fiss_set_obstacles_waymo(self._h, self._stream(stream), _shim.ptr(trajs), _shim.ptr(mask),
-                                                       n, t, int(final_time_step)), "fiss_set_obstacles_waymo")
-        self.num_obstacles = n
+                                                       n, t, int(final_time_step), C.byref(kept)), "fiss_set_obstacles_waymo")
+        self.num_obstacles = int(kept.value)
+        self.obstacle_token += 1
+        return self.num_obstacles
 
     # ------------------------------------------------------------------ host-pointer calls
     def plan_lattice(self, ego: np.ndarray, end: np.ndarray, params: FissParams, want_records: bool = True,

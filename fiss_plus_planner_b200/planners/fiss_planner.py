@@ -221,8 +221,8 @@ class FissPlanner(FrenetOptimalPlanner):
     def _finish_cycle(self):
         order = np.array(self._generated_order, dtype=int)
         idx3 = np.array(np.unravel_index(order, tuple(self.sizes))).T if len(order) else None
-        self.trajs_per_timestep = CandidateBundle(self.engine, self._ego6, self._table[order], self._prm,
-                                                  self._cost[order], self._flags[order], idx3=idx3)
+        self.trajs_per_timestep = self._bundle(self._ego6, self._table[order], self._prm, self._cost[order],
+                                               self._flags[order], idx3=idx3)
         self.all_trajs.append(self.trajs_per_timestep)
         self.trajs_per_timestep = []
 

@@ -48,7 +48,7 @@ class FopPlusPlanner(FrenetOptimalPlanner):
         out = self.engine.plan_grid(ego6[None], self._lattice_grid(), prm, want_records=True, want_volume=True)
         cost, flags = out["cost"][0], out["flags"][0]
         self.stats.num_trajs_generated = len(end)
-        self.all_trajs.append(CandidateBundle(self.engine, ego6, end, prm, cost, flags))
+        self.all_trajs.append(self._bundle(ego6, end, prm, cost, flags))
 
         heap = []
         for seq in range(len(end)):

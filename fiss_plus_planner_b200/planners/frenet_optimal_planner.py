@@ -79,15 +79,27 @@ class ObstacleTable(object):
 
 
 def _rectangle_size(shape):
-    """(length, width) of a CommonRoad ``Rectangle``-like shape; falls back to the extent of its
-    ``shapely_object`` ring about the origin (the only thing the reference reads, :189)."""
+    """(length, width) of a CommonRoad ``Rectangle``-like shape about the origin.  The reference intersects the true
+    ``shapely_object`` (:189); the device predicate is rectangle-vs-rectangle, so anything that is not an axis-aligned
+    rectangle centred on the origin is refused rather than silently replaced by its bounding box."""
+    center = getattr(shape, "center", None)
+    if center is not None and np.any(np.asarray(center, dtype=np.float64) != 0.0):
+        raise NotImplementedError("obstacle shapes with a non-zero center are not supported by the device collision check")
+    if getattr(shape, "orientation", 0.0) not in (0.0, None):
+        raise NotImplementedError("obstacle shapes with a non-zero orientation are not supported by the device collision check")
     if hasattr(shape, "length") and hasattr(shape, "width"):
         return float(shape.length), float(shape.width)
     ring = getattr(shape, "shapely_object", None)
     if ring is not None:
-        pts = np.asarray(getattr(ring, "pts", None) if hasattr(ring, "pts") else ring.exterior.coords)
-        return float(pts[:, 0].max() - pts[:, 0].min()), float(pts[:, 1].max() - pts[:, 1].min())
-    raise TypeError("obstacle_shape must be a rectangle (length/width or shapely_object)")
+        pts = np.asarray(getattr(ring, "pts", None) if hasattr(ring, "pts") else ring.exterior.coords, dtype=np.float64)
+        if len(pts) >= 2 and np.array_equal(pts[0], pts[-1]):
+            pts = pts[:-1]
+        hl, hw = pts[:, 0].max(), pts[:, 1].max()
+        corners = {(-hl, -hw), (-hl, hw), (hl, hw), (hl, -hw)}
+        if len(pts) == 4 and {tuple(v) for v in pts} == corners:
+            return float(2.0 * hl), float(2.0 * hw)
+    raise NotImplementedError("obstacle_shape must be an axis-aligned rectangle about the origin (CommonRoad Rectangle); "
+                              "circles, polygons and shape groups are not supported by the device collision check")
 
 
 def marshal_obstacles(obstacles) -> ObstacleTable:
@@ -125,20 +137,34 @@ class CandidateBundle(collections.abc.Sequence):
     """One cycle's candidates as a lazy sequence of ``FrenetTrajectory``.
 
     Costs and masks are already on the host; the per-step arrays are produced by one
-    ``fiss_eval_end_states_host`` call (full records) the first time an element is touched."""
+    ``fiss_eval_end_states_host`` call (full records) the first time an element is touched.  The bundle remembers the
+    reference line of its cycle (``spline_table`` + the engine's ``spline_token`` at that time): if the engine holds
+    another line by then (a later ``generate_frenet_frame``, another planner on a shared engine) the bundle's own line
+    is re-installed first, so the arrays are never computed against the wrong road."""
 
-    def __init__(self, engine: FissEngine, ego6, end, params, cost, flags, idx3=None):
+    def __init__(self, engine: FissEngine, ego6, end, params, cost, flags, idx3=None, spline_table=None,
+                 spline_token=None):
         self._engine, self._ego6, self._end, self._params = engine, np.array(ego6), np.array(end), params
         self.cost = np.array(cost)
         self.flags = np.array(flags)
         self._idx3 = idx3
         self._items = None
+        self._spline_table = spline_table
+        self._spline_token = engine.spline_token if spline_token is None else spline_token
 
     def __len__(self):
         return len(self.cost)
 
     def _materialize(self):
         if self._items is None:
+            if len(self.cost) == 0:
+                self._items = []
+                return self._items
+            if self._engine.spline_token != self._spline_token:
+                if self._spline_table is None:
+                    raise RuntimeError("the engine's reference line changed since this cycle and the bundle holds no copy")
+                self._engine.set_spline(self._spline_table)   # bumps the token: the owning planner re-installs its own
+                self._spline_token = self._engine.spline_token
             out = self._engine.eval_end_states(self._ego6, self._end, self._params, want_records=True)
             _, _, n_cart = decode_flags(out["flags"])
             items = []
@@ -170,6 +196,10 @@ class FrenetOptimalPlanner(object):
         self._device = device
         self._engine = engine
         self._obstacle_key = None
+        self._obstacle_token = None
+        self._obstacle_ref = None
+        self._spline_table = None
+        self._spline_token = None
         self._lattice_key = None
         self._lattice = None
         self._grid = None
@@ -182,17 +212,48 @@ class FrenetOptimalPlanner(object):
             self._engine = FissEngine(self._device)
         return self._engine
 
+    def _install_spline(self, table):
+        self.engine.set_spline(table)
+        self._spline_table = table
+        self._spline_token = self.engine.spline_token
+
+    def _bundle(self, ego6, end, prm, cost, flags, idx3=None) -> "CandidateBundle":
+        return CandidateBundle(self.engine, ego6, end, prm, cost, flags, idx3=idx3, spline_table=self._spline_table,
+                               spline_token=self._spline_token)
+
+    def invalidate_obstacles(self):
+        """Force the next ``plan()`` to re-marshal the obstacle list (needed only when a prediction object was
+        modified IN PLACE: a different list, or a list whose elements were replaced, is detected by itself)."""
+        self._obstacle_key = None
+
+    @staticmethod
+    def _obstacle_identity(obstacles):
+        if isinstance(obstacles, (list, tuple)):
+            return (id(obstacles), tuple(id(ob) for ob in obstacles))
+        return (id(obstacles), getattr(obstacles, "version", 0))
+
     def _upload_obstacles(self, obstacles):
-        """Predictions are immutable: re-marshal only when the caller passes a different list."""
-        key = (id(obstacles), len(obstacles))
-        if key != self._obstacle_key:
-            tab = marshal_obstacles(obstacles)
-            if len(tab) == 0:
-                self.engine.set_obstacles(None, np.zeros((0, 2)), None, 0)
+        """Scene tables before a cycle.  Predictions are immutable objects, so the list is re-marshalled only when it
+        is a different list or holds different elements (the reference re-reads ``state_at_time`` every cycle, :185-189);
+        the engine's tokens tell when somebody else -- another planner sharing the engine, a lazy candidate bundle --
+        has replaced the tables since, in which case this planner's own are installed again."""
+        eng = self.engine
+        if self._spline_table is not None and eng.spline_token != self._spline_token:
+            self._install_spline(self._spline_table)
+        key = self._obstacle_identity(obstacles)
+        if key != self._obstacle_key or eng.obstacle_token != self._obstacle_token:
+            if hasattr(obstacles, "upload_to"):       # device-ready wire formats (waymo_interface.WaymoObstacles)
+                obstacles.upload_to(eng)
             else:
-                self.engine.set_obstacles(tab.xyth, tab.lw, tab.valid, tab.final_time_step)
+                tab = marshal_obstacles(obstacles)
+                if len(tab) == 0:
+                    eng.set_obstacles(None, np.zeros((0, 2)), None, 0)
+                else:
+                    eng.set_obstacles(tab.xyth, tab.lw, tab.valid, tab.final_time_step)
             self._obstacle_key = key
-            self._obstacle_ref = obstacles  # keep the id alive
+            self._obstacle_token = eng.obstacle_token
+            # keep the list AND its elements alive, so that their ids cannot be reused by new objects
+            self._obstacle_ref = (obstacles, list(obstacles) if isinstance(obstacles, (list, tuple)) else None)
 
     def _end_states(self) -> np.ndarray:
         st = self.settings
@@ -227,12 +288,15 @@ class FrenetOptimalPlanner(object):
         path to rounding (~1e-15 relative)."""
         if fit == "device":
             table = self.engine.fit_splines(np.asarray(centerline_pts, dtype=np.float64)[:, :2], install=0)[0]
+            self._spline_table, self._spline_token = table, self.engine.spline_token
+            self._obstacle_key = None
             self.cubic_spline = CubicSpline2D.from_device_table(table)
             return self.cubic_spline, self.engine.frame_samples(self.cubic_spline.s[-1], 0.1)
         if fit != "host":
             raise ValueError("fit must be 'host' or 'device'")
         self.cubic_spline = CubicSpline2D(centerline_pts[:, 0], centerline_pts[:, 1])
-        self.engine.set_spline(self.cubic_spline.device_table())
+        self._install_spline(self.cubic_spline.device_table())
+        self._obstacle_key = None
         s = np.arange(0, self.cubic_spline.s[-1], 0.1)
         ref_xy = [self.cubic_spline.calc_position(i_s) for i_s in s]
         ref_yaw = [self.cubic_spline.calc_yaw(i_s) for i_s in s]
@@ -253,7 +317,7 @@ class FrenetOptimalPlanner(object):
         self.stats.num_trajs_generated = n_cand
         self.stats.num_trajs_validated = n_cand
         self.stats.num_collison_checks = n_cand
-        self.all_trajs.append(CandidateBundle(self.engine, ego6, end, prm, out["cost"][0], out["flags"][0]))
+        self.all_trajs.append(self._bundle(ego6, end, prm, out["cost"][0], out["flags"][0]))
 
         best = int(out["best_idx"][0])
         if best >= 0:

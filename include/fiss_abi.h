@@ -129,11 +129,16 @@ int32_t fiss_frame_samples_host(fiss_handle* h, void* stream, double step, int32
 int32_t fiss_set_obstacles(fiss_handle* h, void* stream, const double* xyth, const double* lw,
                            const uint8_t* valid, int32_t M, int32_t T_obs, int32_t final_time_step);
 
-/* Same table from the Waymo wire format of waymo_interface.py:24-76,146:
- * trajs [N][T][11] float32 = (x, y, z, l, w, h, heading, vx, vy, valid, type), mask [N][T];
- * an obstacle's prediction ends at the first masked step >= 1 (:49-52); length/width from step 0. */
+/* Same table from the Waymo wire format, with the semantics of convert_waymo_obstacle_to_cr (waymo_interface.py:24-76,146):
+ * trajs [N][T][11] float32 = (x, y, z, l, w, h, heading, vx, vy, valid, type), mask [N][T] (host pointers).
+ * Agent i becomes an obstacle iff mask[i][1] is set (its trajectory, steps 1.. up to the first masked step, :45-54, is
+ * non-empty, :58); a kept agent has states at step 0 (the initial state, never masked, :36-40) through the last unmasked
+ * step of that run and none behind; a dropped agent has no state at all and the agents behind it move up.  Length /
+ * width from step 0 (:33-34).  final_time_step < 0 derives obstacles[0].prediction.final_time_step
+ * (frenet_optimal_planner.py:173) from the FIRST KEPT agent, as the reference's list would; >= 0 overrides it.
+ * n_kept (may be NULL) receives the number of obstacles kept; 0 clears the table (no obstacles: :170-171). */
 int32_t fiss_set_obstacles_waymo(fiss_handle* h, void* stream, const float* trajs, const uint8_t* mask,
-                                 int32_t N, int32_t T, int32_t final_time_step);
+                                 int32_t N, int32_t T, int32_t final_time_step, int32_t* n_kept);
 
 /* ---- device-pointer API ------------------------------------------------------------------- */
 /* The hot kernel: every candidate (b, c) through quintic/quartic solve, n-step evaluation, cost

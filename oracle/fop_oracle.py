@@ -258,13 +258,22 @@ def to_global(tr: Traj, spline: Spline2D, tick: float) -> Traj:
     return tr
 
 
-def passes_constraints(tr: Traj, max_speed: float, max_accel: float) -> bool:
-    """check_constraints (frenet_optimal_planner.py:140-160): speed (signed) and |accel| only."""
+def passes_constraints(tr: Traj, max_speed: float, max_accel: float, max_curvature: float | None = None) -> bool:
+    """check_constraints (frenet_optimal_planner.py:140-160): speed (signed) and |accel| only.  ``max_curvature`` (default
+    off) switches on the first of the three checks the reference carries commented out (:145-146,
+    ``any([abs(c) > self.vehicle.max_curvature for c in traj.c])``) -- north_star's optional curvature mask."""
+    if max_curvature is not None and any([abs(c) > max_curvature for c in tr.c]):
+        return False
     if any([v > max_speed for v in tr.s_d]):
         return False
     if any([abs(a) > max_accel for a in tr.s_dd]):
         return False
     return True
+
+
+def curvature_ok(tr: Traj, max_curvature: float) -> bool:
+    """The curvature check alone (frenet_optimal_planner.py:145-146, commented out in the reference)."""
+    return not any([abs(c) > max_curvature for c in tr.c])
 
 
 class ObstacleTable:
@@ -288,6 +297,43 @@ class ObstacleTable:
                         out.append(sat.place(sat.obstacle_ring(*self.lw[j]), *self.xyth[j, t]))
             self._rings[t] = np.array(out).reshape(-1, 4, 2)
         return self._rings[t]
+
+
+def waymo_obstacle_table(waymo_trajs: np.ndarray, waymo_traj_masks: np.ndarray) -> ObstacleTable | None:
+    """convert_waymo_obstacle_to_cr (planners/waymo_interface/waymo_interface.py:24-76) restated onto the dense table:
+    per agent, the rectangle from row 0 (:33-34), the initial state at step 0 whatever the mask says (:36-40), then states
+    1, 2, ... until the first masked step (``break``, :45-54); an agent whose state list is empty is not appended (:58), so
+    it has no state at any step and the later agents move up.  What the planner then reads off the list:
+    ``obstacles[0].prediction.final_time_step`` = the time step of the first kept agent's last state
+    (frenet_optimal_planner.py:173) and ``state_at_time(t)`` = initial state at 0, trajectory state in [1, t_end], else
+    ``None`` (:187-189; commonroad-io behaviour, restated from memory -- SURVEY 8(f) f-2).  Returns ``None`` for an empty
+    list (``has_collision`` then answers False, :170-171).  Values are widened to float64, as shapely does."""
+    n_obs, n_t, _ = waymo_trajs.shape
+    rows, sizes, valids = [], [], []
+    for i in range(n_obs):
+        traj = waymo_trajs[i]
+        if traj.shape[0] <= 0:
+            continue
+        states = []
+        for t in range(1, n_t):
+            if waymo_traj_masks[i, t]:
+                states.append(t)
+            else:
+                break
+        if states:
+            valid = np.zeros(n_t, dtype=bool)
+            valid[0] = True
+            valid[states] = True
+            xyth = np.zeros((n_t, 3))
+            for t in np.flatnonzero(valid):
+                xyth[t] = (float(traj[t, 0]), float(traj[t, 1]), float(traj[t, 6]))
+            rows.append(xyth)
+            sizes.append((float(traj[0, 3]), float(traj[0, 4])))
+            valids.append(valid)
+    if not rows:
+        return None
+    final_time_step = int(np.flatnonzero(valids[0])[-1])
+    return ObstacleTable(np.array(rows), np.array(sizes), np.array(valids), final_time_step)
 
 
 def has_collision(tr: Traj, obs: ObstacleTable | None, ego_ring: np.ndarray, now: int, check_res: int = 2) -> bool:
@@ -671,7 +717,7 @@ PLANNERS = {"FOP": FopOracle, "FOP+": FopPlusOracle, "FISS": FissOracle, "FISS+"
 
 # ----------------------------------------------------------------------------------- dense API
 def dense_lattice_eval(ego6, lattice, spline: Spline2D, obs: ObstacleTable | None, *, tick, target_speed,
-                       max_speed, max_accel, ego_l, ego_w, now=0):
+                       max_speed, max_accel, ego_l, ego_w, now=0, max_curvature=None):
     """Every candidate of ``lattice`` [(d, v, T)...] through the whole path; returns the arrays the
     GPU parity tests compare: cost, n, n', constraint-ok, collision, winner (last minimal survivor)."""
     ring = sat.ego_ring(ego_l, ego_w)
@@ -683,7 +729,7 @@ def dense_lattice_eval(ego6, lattice, spline: Spline2D, obs: ObstacleTable | Non
     cost = np.array([tr.cost_final for tr in trajs])
     n = np.array([len(tr.t) for tr in trajs])
     n_cart = np.array([len(tr.x) for tr in trajs])
-    ok = np.array([passes_constraints(tr, max_speed, max_accel) for tr in trajs])
+    ok = np.array([passes_constraints(tr, max_speed, max_accel, max_curvature) for tr in trajs])
     coll = np.array([has_collision(tr, obs, ring, now) for tr in trajs])
     best, lo = -1, float("inf")
     for i in range(len(trajs)):

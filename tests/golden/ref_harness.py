@@ -245,3 +245,50 @@ def attach_shapely_shapes(scenario):
         if not hasattr(sh, "shapely_object"):
             sh.shapely_object = RefRectangle(sh.length, sh.width).shapely_object
     return scenario
+
+
+def load_reference_waymo():
+    """Import the reference's ``planners/waymo_interface/waymo_interface.py`` UNMODIFIED and return the module
+    (``convert_waymo_obstacle_to_cr``, :24-76, is what the f-3 goldens execute).  The script's imports resolve to:
+    commonroad-io names -> the stand-ins of commonroad_lite (as for the closed-loop driver); ``fiss_planner.*`` -- a
+    stale import path that does not exist in the reference tree (:22) -- and matplotlib -> inert modules; everything
+    else (``common.vehicle.vehicle``, ``common.scenario.frenet``) is the reference's own code."""
+    install_driver_stubs()
+    import importlib
+    from fiss_plus_planner_b200.planners.commonroad_interface import commonroad_lite as crl
+    sys.modules["commonroad.scenario.state"].InitialState = crl.InitialState
+    sys.modules["commonroad.scenario.obstacle"].Obstacle = type("Obstacle", (), {})
+    stale = {}
+    for name in ("fiss_planner", "fiss_planner.fiss_plus_planner"):
+        m = types.ModuleType(name)
+        m.FissPlusPlannerSettings = type("FissPlusPlannerSettings", (), {})
+        m.FissPlusPlanner = type("FissPlusPlanner", (), {})
+        stale[name] = sys.modules.get(name)
+        sys.modules[name] = m
+    sys.modules["fiss_planner"].fiss_plus_planner = sys.modules["fiss_planner.fiss_plus_planner"]
+    try:
+        return importlib.import_module("planners.waymo_interface.waymo_interface")
+    finally:
+        for name, old in stale.items():
+            if old is None:
+                sys.modules.pop(name, None)
+            else:
+                sys.modules[name] = old
+
+
+def table_from_obstacle_objects(obstacles, t_obs):
+    """Read a list of CommonRoad-style obstacle objects the way ``has_collision`` does (:173,185-189):
+    ``(xyth [M, t_obs, 3], lw [M, 2], valid [M, t_obs], obstacles[0].prediction.final_time_step)``."""
+    m = len(obstacles)
+    xyth = np.zeros((m, t_obs, 3))
+    valid = np.zeros((m, t_obs), dtype=bool)
+    lw = np.zeros((m, 2))
+    for j, ob in enumerate(obstacles):
+        lw[j] = (ob.obstacle_shape.length, ob.obstacle_shape.width)
+        for t in range(t_obs):
+            st = ob.state_at_time(t)
+            if st is not None:
+                xyth[j, t] = (st.position[0], st.position[1], st.orientation)
+                valid[j, t] = True
+    final = int(obstacles[0].prediction.final_time_step) if m else 0
+    return xyth, lw, valid, final

@@ -26,7 +26,7 @@ def test_header_symbols_are_exported(lib):
     for name in declared:
         assert hasattr(lib, name), f"{name} declared in fiss_abi.h but not exported"
     assert declared == set(_shim.EXPORTS)
-    assert lib.fiss_abi_version() == 1
+    assert lib.fiss_abi_version() == 2
 
 
 def test_params_struct_layout():

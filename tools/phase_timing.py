@@ -1,8 +1,8 @@
 #!/usr/bin/env python
 """Per-stage cycle split of the lattice kernel (debug build with -DFISS_PHASE_TIMING; GPU box):
 
-    python -m fiss_plus_planner_b200.build --out=build/libfiss_phase.so -DFISS_PHASE_TIMING
-    FISSGPU_LIB=$PWD/build/libfiss_phase.so python tools/phase_timing.py
+    python -m fiss_plus_planner_b200.build --out=build/other/libfiss_phase.so -DFISS_PHASE_TIMING
+    FISSGPU_LIB=$PWD/build/other/libfiss_phase.so python tools/phase_timing.py
 
 Thread 0 of every CTA accumulates clock64() deltas between the stage barriers; the sums over CTAs are printed as
 shares of the CTA-resident time, for the materialising and the winner-only variants of the cfg4 workload."""
