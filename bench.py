@@ -12,15 +12,19 @@ configs[3] per-GPU shard: 512 ego states per GPU, weak scaling -> 4096 on 8 GPUs
               HBM, FP64: 276 MB per step per GPU, larger than the 126 MB L2) + the record kernel (the pick
               fused in: argmin per ego state, then the winners' full records).  CUDA events on the launching
               stream, max over ranks.
-* ``e2e``     the same metric through the host C-ABI call ``fiss_plan_grid_host`` with HOST buffers:
-              H2D of the ego states and D2H of winners/records inside the timed region.
+* ``e2e``     the same metric through the host C-ABI with HOST buffers, H2D of the ego states and D2H of winners /
+              records inside the timed region, every step: the streaming pair ``fiss_plan_grid_submit`` /
+              ``fiss_plan_grid_wait`` (two lanes: the copy-back of step k under the kernels of step k+1);
+              ``value_sync_call`` = one blocking ``fiss_plan_grid_host`` per step.  This path runs the WINNER-ONLY lattice
+              kernel + the winners' records (what plan() returns), not the materialising kernel ``value`` times.
 * ``roofline`` the lattice kernel alone: algorithmic bytes (SURVEY 8(d) formula) / its CUDA-event time,
               against MEASURED_PEAKS.json's HBM copy bandwidth.  The kernel is FP64-issue bound, not
               HBM bound: the fraction is reported as measured, not dressed up.
-* ``cpu_baseline`` the oracle port of the reference's Python path (oracle/fop_oracle.py), all host cores.
+* ``cpu_baseline`` the reference's CPU path on all host cores: a Pool over independent ego states, one whole plan()
+              per task -- the unmodified reference where /root/reference is mounted, else the oracle port.
 
-``--impl reference`` times that CPU port alone (the reference itself is Python + commonroad/shapely
-and cannot travel to the GPU box; its hot path is restated in oracle/, pinned by tests/golden).
+``--impl reference`` times that CPU path alone (the reference is Python + commonroad/shapely with nothing to
+install and cannot travel to the GPU box, where its hot path runs as restated in oracle/, pinned by tests/golden).
 """
 from __future__ import annotations
 
@@ -90,39 +94,97 @@ def config_dict(n_gpus, batch_per_gpu):
 
 
 # ------------------------------------------------------------------------------------------------ CPU baseline
-def cpu_port_rate(sc, steps: int, warmup: int, budget_s: float):
-    """Candidates/s of the oracle port on all host cores.  One step = ONE ego state's 270-candidate
-    lattice split across the cores (FOP plan() semantics)."""
+REFERENCE_ROOT = "/root/reference"
+_CPU = {}
+
+
+def _cpu_worker_init(kind, centerline, obs_arrays, lattice, min_t, max_t, max_target_speed, ego_l, ego_w, v_max, a_max):
+    """Per-process set-up (spline fit, obstacle objects), outside the timed region: ``kind`` = "reference" builds the
+    UNMODIFIED reference's FrenetOptimalPlanner from /root/reference (tests/golden/ref_harness.py: commonroad symbols
+    stubbed, NumPy SAT in place of shapely/GEOS); "port" builds oracle/fop_oracle.py's restatement of it."""
+    import warnings as _w
+    _w.filterwarnings("ignore")
+    if kind == "reference":
+        sys.path.insert(0, os.path.join(ROOT, "tests", "golden"))
+        import ref_harness as rh
+        ref = rh.load_reference()
+        veh = ref.Vehicle(rh.make_vehicle_params(l=ego_l, w=ego_w, v_max=v_max, a_max=a_max))
+        st = ref.FrenetOptimalPlannerSettings(*lattice)
+        st.min_t, st.max_t = min_t, max_t
+        pl = ref.FrenetOptimalPlanner(st, veh)
+        pl.generate_frenet_frame(centerline)
+        obstacles = rh.make_ref_obstacles(*obs_arrays)
+        _CPU.update(kind=kind, pl=pl, obstacles=obstacles, speed=max_target_speed,
+                    state=lambda e: ref.FrenetState(0.0, e[0], e[1], e[2], 0.0, e[3], e[4], e[5], 0.0))
+    else:
+        from oracle import fop_oracle as fo
+        st = fo.Settings(*lattice)
+        st.min_t, st.max_t, st.highest_speed = min_t, max_t, max_target_speed
+        pl = fo.FopOracle(st, ego_l, ego_w, v_max, a_max)
+        pl.generate_frenet_frame(centerline)
+        _CPU.update(kind=kind, pl=pl, obstacles=fo.ObstacleTable(*obs_arrays), speed=max_target_speed)
+
+
+def _cpu_worker_plan(ego6):
+    """One whole planning problem: FrenetOptimalPlanner.plan() of one ego state (frenet_optimal_planner.py:247-270)."""
+    pl = _CPU["pl"]
+    if _CPU["kind"] == "reference":
+        pl.plan(_CPU["state"](ego6), _CPU["speed"], _CPU["obstacles"], 0)
+        n = len(pl.all_trajs[-1])
+        pl.all_trajs.clear()
+        return n
+    pl.plan(tuple(ego6), _CPU["speed"], _CPU["obstacles"], 0)
+    return len(pl.last_all)
+
+
+def cpu_kind():
+    """The real reference when its tree is mounted (this container), else the oracle port (the GPU box)."""
+    forced = os.environ.get("FISS_BENCH_CPU_KIND")      # "port" / "reference": for comparing the two in one place
+    if forced in ("port", "reference"):
+        return forced
+    return "reference" if os.path.isdir(os.path.join(REFERENCE_ROOT, "planners")) else "port"
+
+
+def cpu_rate(sc, steps: int, warmup: int, budget_s: float, min_s: float = 5.0):
+    """Candidates/s of the reference's CPU path on all host cores: a ``multiprocessing.Pool`` over
+    INDEPENDENT ego states, one whole plan() per task -- the reference itself is single-threaded, so this is how a user
+    would fill the host.  One step = one ego state per worker.  At least ``min_s`` seconds are sampled (more steps than
+    asked if need be) and at most ``budget_s``."""
     from fiss_plus_planner_b200 import synthetic as syn
-    from oracle import fop_oracle as fo
-    cores = os.cpu_count() or 1
+    kind = cpu_kind()
+    workers = os.cpu_count() or 1
     n_cand = LATTICE[0] * LATTICE[1] * LATTICE[2]
-    workers = min(cores, n_cand)
-    bounds = np.linspace(0, n_cand, workers + 1).astype(int)
-    init = (sc.centerline, (sc.obs.xyth, sc.obs.lw, sc.obs.valid, sc.obs.final_time_step),
-            dict(num_width=LATTICE[0], num_speed=LATTICE[1], num_t=LATTICE[2]), MIN_T, MAX_T, sc.max_target_speed,
-            syn.EGO_L, syn.EGO_W, syn.EGO_V_MAX, syn.EGO_A_MAX)
+    init = (kind, sc.centerline, (sc.obs.xyth, sc.obs.lw, sc.obs.valid, sc.obs.final_time_step), LATTICE, MIN_T, MAX_T,
+            sc.max_target_speed, syn.EGO_L, syn.EGO_W, syn.EGO_V_MAX, syn.EGO_A_MAX)
     ctx = mp.get_context("fork")
-    times = []
-    with ctx.Pool(workers, initializer=fo.baseline_worker_init, initargs=init) as pool:
+    times, cands = [], 0
+    with ctx.Pool(workers, initializer=_cpu_worker_init, initargs=init) as pool:
         t_begin = time.perf_counter()
-        for i in range(warmup + steps):
-            ego6 = tuple(float(v) for v in sc.ego[i % len(sc.ego)])
-            tasks = [(ego6, int(bounds[w]), int(bounds[w + 1]), 0) for w in range(workers)]
+        i = 0
+        while True:
+            egos = [tuple(float(v) for v in sc.ego[(i * workers + w) % len(sc.ego)]) for w in range(workers)]
             t0 = time.perf_counter()
-            res = pool.map(fo.baseline_worker_slice, tasks, chunksize=1)
+            res = pool.map(_cpu_worker_plan, egos, chunksize=1)
             dt = time.perf_counter() - t0
-            assert sum(r[0] for r in res) == n_cand
+            assert all(r == n_cand for r in res)
             if i >= warmup:
                 times.append(dt)
-            if time.perf_counter() - t_begin > budget_s and len(times) >= 1:
+                cands += sum(res)
+            i += 1
+            elapsed = time.perf_counter() - t_begin
+            if elapsed > budget_s and times:
+                break
+            if len(times) >= steps and sum(times) >= min_s:
                 break
     total = float(np.sum(times))
-    return dict(value=n_cand * len(times) / total, steps_done=len(times), ms_per_step=1e3 * total / len(times),
-                cores=workers,
-                sample="%d step(s); each = one ego state's %d-candidate lattice (n<=%d, %d obstacles) split over %d "
-                       "processes; Python port of the reference loops, NumPy SAT in place of shapely/GEOS"
-                       % (len(times), n_cand, int(np.ceil(MAX_T / 0.1)), NUM_OBS, workers))
+    what = ("the UNMODIFIED reference FrenetOptimalPlanner.plan() from /root/reference (commonroad symbols stubbed, NumPy SAT "
+            "in place of shapely/GEOS)" if kind == "reference" else
+            "oracle/fop_oracle.py, the line-by-line Python port of the reference's plan() (pinned bit-exact to it by "
+            "tests/golden; NumPy SAT in place of shapely/GEOS)")
+    return dict(value=cands / total, steps_done=len(times), ms_per_step=1e3 * total / len(times), cores=workers, kind=kind,
+                sample="%d step(s) in %.1f s; each = %d independent ego states, one whole plan() per process (%d-candidate "
+                       "lattice, n<=%d, %d obstacles); %s" % (len(times), total, workers, n_cand, int(np.ceil(MAX_T / 0.1)),
+                                                             NUM_OBS, what))
 
 
 # ------------------------------------------------------------------------------------------------ clocks
@@ -288,10 +350,20 @@ def run_ours(args):
     bpg = args.batch_per_gpu
     sc = make_workload(n_gpus, bpg)
 
+    # each rank stays on its own slice of the host cores (8 ranks + NCCL / sampler threads migrating over one NUMA node
+    # is what a 2.7 ms timed region does not forgive)
+    try:
+        avail = sorted(os.sched_getaffinity(0))
+        per = len(avail) // max(world, 1)
+        if world > 1 and per >= 2:
+            os.sched_setaffinity(0, set(avail[local_rank * per:(local_rank + 1) * per]))
+    except (AttributeError, OSError):
+        pass
+
     # CPU baseline first (rank 0, N=1 only), before CUDA is initialised in this process (fork-safe)
     cpu = None
     if n_gpus == 1 and not args.no_cpu_baseline:
-        cpu = cpu_port_rate(sc, steps=args.cpu_steps, warmup=1, budget_s=40.0)
+        cpu = cpu_rate(sc, steps=args.cpu_steps, warmup=1, budget_s=40.0)
 
     from fiss_plus_planner_b200.engine import FissEngine, fop_grid, make_params
     from fiss_plus_planner_b200.planners.common.cost.cost_function import CostFunction
@@ -301,6 +373,11 @@ def run_ours(args):
 
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    # the clock sampler runs from here on: nvidia-smi's start-up (NVML initialisation over every GPU of the box) must not
+    # fall into a timed region
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
     veh = Vehicle(syn.vehicle_params())
     st = FrenetOptimalPlannerSettings(*LATTICE)
     st.min_t, st.max_t, st.highest_speed = MIN_T, MAX_T, sc.max_target_speed
@@ -318,7 +395,6 @@ def run_ours(args):
     sptr = stream.cuda_stream
     f64 = torch.float64
     ego_t = torch.tensor(ego, dtype=f64, device=dev)
-    end_t = torch.tensor(end, dtype=f64, device=dev)
     cost_t = torch.empty(B * C, dtype=f64, device=dev)
     flags_t = torch.empty(B * C, dtype=torch.int32, device=dev)
     mat_t = torch.empty((5, B * C, n_stride), dtype=f64, device=dev)
@@ -328,8 +404,8 @@ def run_ours(args):
     meta_t = torch.empty((B, 2), dtype=torch.int32, device=dev)
 
     def step_device(mat=mat_t):
-        eng.eval_grid_dev(ego_t, grid, prm, cost_t, flags_t, mat, n_stride, stream=sptr)
-        eng.pick_winners_dev(ego_t, end_t, prm, cost_t, flags_t, bidx_t, bcost_t, rec_t, meta_t, n_stride, stream=sptr)
+        # ONE call = one plan step: lattice kernel + record kernel (pick fused in); one cudaGraphLaunch from the 2nd call on
+        eng.plan_grid_dev(ego_t, grid, prm, cost_t, flags_t, mat, bidx_t, bcost_t, meta_t, rec_t, n_stride, stream=sptr)
 
     def barrier():
         if world > 1:
@@ -343,54 +419,74 @@ def run_ours(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
-    # ---- device-resident timing (value) + the lattice kernel alone (roofline)
-    for _ in range(args.warmup):
-        step_device()
-    barrier()
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()
+    def timed_steps(fn):
+        """K steps between two events (the headline) with one event after every step (the per-step spread)."""
+        for _ in range(args.warmup):
+            fn()
+        barrier()
+        marks = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
+        marks[0].record(stream)
+        for i in range(args.steps):
+            fn()
+            marks[i + 1].record(stream)
+        barrier()
+        total = marks[0].elapsed_time(marks[-1])
+        per = [marks[i].elapsed_time(marks[i + 1]) for i in range(args.steps)]
+        return max_over_ranks(total), max_over_ranks(float(np.median(per)))
+
+    # ---- device-resident timing (value): full materialisation + pick + winners' records
+    time.sleep(0.5 if rank == 0 else 0.0)     # let the sampler's start-up pass
     launches0 = eng.launch_count
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    total_ms, median_ms = timed_steps(step_device)
+    launches = (eng.launch_count - launches0) * args.steps // (args.steps + args.warmup)
+
+    # ---- the lattice kernel alone (roofline): CUDA events around every launch, same buffers
+    for _ in range(args.warmup):
+        eng.eval_grid_dev(ego_t, grid, prm, cost_t, flags_t, mat_t, n_stride, stream=sptr)
+    barrier()
     k_ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
-    ev0.record(stream)
     for i in range(args.steps):
         k_ev[i][0].record(stream)
         eng.eval_grid_dev(ego_t, grid, prm, cost_t, flags_t, mat_t, n_stride, stream=sptr)
         k_ev[i][1].record(stream)
-        eng.pick_winners_dev(ego_t, end_t, prm, cost_t, flags_t, bidx_t, bcost_t, rec_t, meta_t, n_stride, stream=sptr)
-    ev1.record(stream)
     barrier()
-    launches = eng.launch_count - launches0
-    total_ms = max_over_ranks(ev0.elapsed_time(ev1))
-    kern_ms = float(np.mean([a.elapsed_time(b) for a, b in k_ev]))
+    k_times = [a.elapsed_time(b) for a, b in k_ev]
+    kern_ms, kern_median_ms = float(np.mean(k_times)), float(np.median(k_times))
 
     # ---- winner-only mode (what plan() strictly needs; reported beside the headline)
-    for _ in range(args.warmup):
-        step_device(None)
-    barrier()
-    ev0.record(stream)
-    for _ in range(args.steps):
-        step_device(None)
-    ev1.record(stream)
-    barrier()
-    wo_ms = max_over_ranks(ev0.elapsed_time(ev1))
+    wo_ms, wo_median_ms = timed_steps(lambda: step_device(None))
 
-    # ---- end to end through the host C-ABI call (H2D + kernels + D2H inside).  Host buffers are page-locked
-    # (engine.pinned_empty / alloc_plan_outputs): the call DMAs the ego states straight from `ego_pin` and the
-    # winners + records straight into `outs`, every step.
+    # ---- end to end through the host C-ABI (H2D + kernels + D2H inside the timed region, every step), page-locked host
+    # buffers (engine.pinned_empty / alloc_plan_outputs).  (a) streaming: fiss_plan_grid_submit / _wait on two lanes, the
+    # copy-back of step k under the kernels of step k + 1 -- how a caller with a sequence of batches drives it;
+    # (b) one synchronous fiss_plan_grid_host call per step.
     ego_pin = eng.pinned_empty(ego.shape, np.float64)
     ego_pin[...] = ego
-    outs = eng.alloc_plan_outputs(B, grid, want_records=True, want_volume=False, pinned=True)
+    outs = [eng.alloc_plan_outputs(B, grid, want_records=True, want_volume=False, pinned=True) for _ in range(2)]
+
+    def e2e_stream(k_steps):
+        eng.plan_grid_submit(0, ego_pin, grid, prm, outs[0], stream=sptr)
+        for k in range(1, k_steps + 1):
+            if k < k_steps:
+                eng.plan_grid_submit(k % 2, ego_pin, grid, prm, outs[k % 2], stream=sptr)
+            eng.plan_grid_wait((k - 1) % 2)
+
+    e2e_stream(args.warmup)
+    barrier()
+    t0 = time.perf_counter()
+    e2e_stream(args.steps)
+    torch.cuda.synchronize()
+    e2e_s = max_over_ranks(time.perf_counter() - t0)
+    assert int(outs[(args.steps - 1) % 2]["best_idx"][0]) == int(bidx_t[0].item())   # the device-resident path's winners
     for _ in range(args.warmup):
-        eng.plan_grid(ego_pin, grid, prm, want_records=True, want_volume=False, stream=sptr, out=outs)
+        eng.plan_grid(ego_pin, grid, prm, want_records=True, want_volume=False, stream=sptr, out=outs[0])
     barrier()
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        out = eng.plan_grid(ego_pin, grid, prm, want_records=True, want_volume=False, stream=sptr, out=outs)
+        out = eng.plan_grid(ego_pin, grid, prm, want_records=True, want_volume=False, stream=sptr, out=outs[0])
     torch.cuda.synchronize()
-    e2e_s = max_over_ranks(time.perf_counter() - t0)
-    assert int(out["best_idx"][0]) == int(bidx_t[0].item())      # the same winners as the device-resident path
+    e2e_sync_s = max_over_ranks(time.perf_counter() - t0)
+    assert int(out["best_idx"][0]) == int(bidx_t[0].item())
     # and once more with ordinary pageable NumPy buffers (staged through the handle's pinned bounce buffer)
     for _ in range(args.warmup):
         eng.plan_grid(ego, grid, prm, want_records=True, want_volume=False, stream=sptr)
@@ -400,7 +496,7 @@ def run_ours(args):
         eng.plan_grid(ego, grid, prm, want_records=True, want_volume=False, stream=sptr)
     torch.cuda.synchronize()
     e2e_pageable_s = max_over_ranks(time.perf_counter() - t0)
-    # the clock record spans all three timed regions (device-resident, winner-only, end-to-end)
+    # the clock record spans all timed regions (device-resident, kernel alone, winner-only, end-to-end)
     clocks = sampler.stop() if rank == 0 else None
     h2d = B * 48
     d2h = B * (8 + 4 + 8) + B * 16 * n_stride * 8
@@ -412,12 +508,13 @@ def run_ours(args):
         eng2 = FissEngine(local_rank)
         eng2.set_spline(sc2.spline.device_table())
         eng2.set_obstacles(sc2.obs.xyth, sc2.obs.lw, sc2.obs.valid, sc2.obs.final_time_step)
+        out2 = eng2.alloc_plan_outputs(1, grid, want_records=True, want_volume=True, pinned=False)   # reused, as plan() does
         for _ in range(20):
-            eng2.plan_grid(sc2.ego[:1], grid, prm, want_records=True, want_volume=True, stream=sptr)
+            eng2.plan_grid(sc2.ego[:1], grid, prm, want_records=True, want_volume=True, stream=sptr, out=out2)
         lat = []
-        for _ in range(200):
+        for _ in range(400):
             t1 = time.perf_counter()
-            eng2.plan_grid(sc2.ego[:1], grid, prm, want_records=True, want_volume=True, stream=sptr)
+            eng2.plan_grid(sc2.ego[:1], grid, prm, want_records=True, want_volume=True, stream=sptr, out=out2)
             lat.append(time.perf_counter() - t1)
         p50 = 1e3 * float(np.median(lat))
         eng2.close()
@@ -445,28 +542,37 @@ def run_ours(args):
         line = {
             "metric": METRIC, "value": cand_total * args.steps / (total_ms * 1e-3), "unit": UNIT,
             "n_gpus": n_gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": total_ms / args.steps,
+            "ms_per_step_median": median_ms,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": config_dict(n_gpus, bpg),
             "mode": "full materialisation (x,y,yaw,v,kappa of every candidate to HBM, FP64) + pick + winner records",
             "value_winner_only": cand_total * args.steps / (wo_ms * 1e-3),
             "e2e": {"value": cand_total * args.steps / e2e_s, "unit": UNIT, "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": d2h, "ms_per_step": 1e3 * e2e_s / args.steps,
-                    "call": "fiss_plan_grid_host (pinned host ego states in, winners + full records out to pinned host)",
+                    "mode": "winner-only lattice kernel + the winners' full records (NOT the materialising kernel that "
+                            "`value` and `roofline` time): what plan() returns",
+                    "call": "fiss_plan_grid_submit / fiss_plan_grid_wait, two lanes: pinned host ego states in, winners + "
+                            "full records out to pinned host every step, the copy-back of step k under the kernels of "
+                            "step k+1",
+                    "value_sync_call": cand_total * args.steps / e2e_sync_s,
+                    "sync_call": "one blocking fiss_plan_grid_host per step (no overlap between steps)",
                     "value_pageable_buffers": cand_total * args.steps / e2e_pageable_s},
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic, "traffic_source": traffic_src,
                          "kernel": "fiss_grid_kernel<yaw> (materialising)", "kernel_ms": kern_ms,
+                         "kernel_ms_median": kern_median_ms,
                          "algorithmic_bytes_per_launch": alg, "peak_source": peak_src,
                          "note": "FP64-issue bound by arithmetic (SURVEY 8(d)); see profiles/ for ncu fp64 pipe utilisation"},
             "plan_cycle_p50_ms": p50,
-            "plan_cycle_config": "config 2: 1 ego state, 270 candidates, 8 obstacles, fiss_plan_grid_host incl. H2D/D2H",
+            "plan_cycle_config": "config 2: 1 ego state, 270 candidates, 8 obstacles, fiss_plan_grid_host incl. H2D/D2H of the "
+                                 "winner, its full record and the whole cost / flags volume (the two kernels as one CUDA-graph launch)",
             "clocks": clocks,
         }
         if closed is not None:
             line["closed_loop"] = closed
         if cpu is not None:
-            line["cpu_baseline"] = {"value": cpu["value"], "unit": UNIT, "cores": cpu["cores"], "kind": "port",
+            line["cpu_baseline"] = {"value": cpu["value"], "unit": UNIT, "cores": cpu["cores"], "kind": cpu["kind"],
                                     "sample": cpu["sample"]}
         if saved_stdout is not None:
             sys.stdout.flush()
@@ -479,25 +585,29 @@ def run_ours(args):
 
 # ------------------------------------------------------------------------------------------------ reference arm
 def run_reference(args):
+    """The reference arm: the reference's own CPU implementation of the path on the box's host cores, same config /
+    metric / unit.  Where /root/reference is mounted (the build container) that is the UNMODIFIED
+    ``FrenetOptimalPlanner.plan()`` (kind "reference"); on the GPU box -- the reference is pure Python with no installable
+    package and cannot travel -- it is oracle/fop_oracle.py, the port pinned bit-exact to it (kind "port")."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     n_gpus = int(os.environ.get("WORLD_SIZE", str(args.gpus)))
-    sc = make_workload(1, min(args.batch_per_gpu, 64))
+    sc = make_workload(1, min(args.batch_per_gpu, 512))
     # keep the whole run within a few minutes whatever K and W are
-    cpu = cpu_port_rate(sc, steps=args.steps, warmup=args.warmup, budget_s=150.0)
+    cpu = cpu_rate(sc, steps=args.steps, warmup=args.warmup, budget_s=150.0)
     line = {
         "impl": "reference", "metric": METRIC, "value": cpu["value"], "unit": UNIT, "n_gpus": n_gpus,
         "steps": cpu["steps_done"], "warmup": args.warmup, "ms_per_step": cpu["ms_per_step"],
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": config_dict(n_gpus, args.batch_per_gpu),
-        "cpu_baseline": {"value": cpu["value"], "unit": UNIT, "cores": cpu["cores"], "kind": "port",
+        "cpu_baseline": {"value": cpu["value"], "unit": UNIT, "cores": cpu["cores"], "kind": cpu["kind"],
                          "sample": cpu["sample"]},
         "e2e": {"value": cpu["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
-        "note": "the reference is pure Python + commonroad/shapely (not installable here, cannot travel): this arm "
-                "times its hot path as restated in oracle/fop_oracle.py (pinned bit-exact to the reference by "
-                "tests/golden), on all host cores",
+        "note": "the reference is pure Python + commonroad/shapely with no package to install (no setup.py / pyproject): "
+                "baseline/_ref cannot exist.  kind=reference: its own plan() imported from /root/reference; kind=port: "
+                "oracle/fop_oracle.py (pinned bit-exact to the reference by tests/golden) where that tree is absent",
     }
     print(json.dumps(line))
 
@@ -513,8 +623,8 @@ def main():
     ap.add_argument("--workload", default="cfg4", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-closed-loop", action="store_true", help="skip the config-1 closed-loop latency section")
-    ap.add_argument("--cpu-steps", type=int, default=150,
-                    help="CPU-baseline sample: lattices evaluated by the oracle port (150 x ~80 ms = ~12 s of host time)")
+    ap.add_argument("--cpu-steps", type=int, default=6,
+                    help="CPU-baseline sample: steps of one whole plan() per host core (6 x ~2 s = ~12 s of host time)")
     args = ap.parse_args()
     args.batch_per_gpu = select_workload(args.workload, args.batch_per_gpu)
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup

@@ -23,6 +23,7 @@ EXPORTS = (
     "fiss_set_spline", "fiss_fit_splines_host", "fiss_frame_samples_host", "fiss_set_obstacles", "fiss_set_obstacles_waymo",
     "fiss_eval_candidates_dev", "fiss_eval_grid_dev", "fiss_pick_winners_dev", "fiss_full_records_dev",
     "fiss_plan_lattice_host", "fiss_plan_grid_host", "fiss_eval_end_states_host", "fiss_launch_count",
+    "fiss_plan_grid_dev", "fiss_plan_grid_submit", "fiss_plan_grid_wait",
 )
 
 
@@ -90,6 +91,9 @@ def load():
         "fiss_plan_lattice_host": (i32, [vp, vp, vp, i32, vp, i32, pp, vp, vp, vp, vp, i32, vp, vp]),
         "fiss_eval_end_states_host": (i32, [vp, vp, vp, vp, i32, pp, vp, vp, vp, i32]),
         "fiss_launch_count": (C.c_int64, [vp]),
+        "fiss_plan_grid_dev": (i32, [vp, vp, vp, i32, gp, pp, vp, vp, vp, vp, vp, vp, vp, i32]),
+        "fiss_plan_grid_submit": (i32, [vp, vp, i32, vp, i32, gp, pp, vp, vp, vp, vp, i32]),
+        "fiss_plan_grid_wait": (i32, [vp, i32]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(lib, name)

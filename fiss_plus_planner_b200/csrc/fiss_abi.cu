@@ -68,6 +68,89 @@ constexpr int kMaxParts = 4;                   // plan_common: pieces a big batc
 constexpr size_t kSmemLimit = 227 * 1024;      // opt-in maximum per CTA on sm_100
 constexpr size_t kSmemObsBudget = 100 * 1024;  // stage obstacle rows only while 2 CTAs/SM still fit
 
+// One kernel launch as data: what the planning code decided (function, shape, arguments).  It is either issued on a
+// stream right away or becomes a kernel node of a CUDA graph (StepGraph) whose parameters are patched from call to call.
+struct KernelLaunch {
+  const void* func = nullptr;
+  dim3 grid{1, 1, 1}, block{1, 1, 1};
+  size_t smem = 0;
+  bool pdl = false;  // programmatic dependent launch behind the previous kernel (direct launches only)
+  int n_params = 0;
+  uint16_t off[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  size_t arg_bytes = 0;
+  alignas(16) unsigned char arg[1024];
+  template <typename T>
+  void push(const T& v) {
+    static_assert(sizeof(T) <= sizeof(arg), "kernel argument too large");
+    size_t o = (arg_bytes + alignof(T) - 1) & ~(alignof(T) - 1);
+    std::memcpy(arg + o, &v, sizeof(T));
+    off[n_params++] = (uint16_t)o;
+    arg_bytes = o + sizeof(T);
+  }
+  void params(void** out) {
+    for (int i = 0; i < n_params; ++i) out[i] = arg + off[i];
+  }
+  bool same_shape(const KernelLaunch& o) const {
+    return grid.x == o.grid.x && block.x == o.block.x && smem == o.smem;
+  }
+  bool same_args(const KernelLaunch& o) const {
+    return arg_bytes == o.arg_bytes && std::memcmp(arg, o.arg, arg_bytes) == 0;
+  }
+};
+
+// A plan step as an instantiated CUDA graph: [H2D of the inputs] -> kernels in order -> [D2H of the results].  Built
+// once per topology (same kernels, same copy endpoints); afterwards a call only patches the kernel nodes whose launch
+// shape or arguments changed (cudaGraphExecKernelNodeSetParams: time_step_now moves every cycle of a closed loop) and
+// launches the whole step with ONE cudaGraphLaunch.
+struct StepGraph {
+  cudaGraph_t graph = nullptr;
+  cudaGraphExec_t exec = nullptr;
+  std::vector<cudaGraphNode_t> knodes;
+  std::vector<KernelLaunch> kl;
+  const void* h2d_src = nullptr;
+  void* h2d_dst = nullptr;
+  size_t h2d_bytes = 0;
+  const void* d2h_src = nullptr;
+  void* d2h_dst = nullptr;
+  size_t d2h_bytes = 0;
+  int64_t launches = 0, rebuilds = 0, patches = 0;
+  void release() {
+    if (exec) cudaGraphExecDestroy(exec);
+    if (graph) cudaGraphDestroy(graph);
+    exec = nullptr;
+    graph = nullptr;
+    knodes.clear();
+    kl.clear();
+  }
+};
+
+// One in-flight call of the streaming entry points (fiss_plan_grid_submit / _wait): its own device buffers, pinned
+// bounce buffers and events, so that the copy-back of one lane runs under the kernels of the other.
+constexpr int kLanes = 2;
+struct Lane {
+  DevBuf d_ego, d_cost, d_flags, d_win, d_records;
+  PinBuf h_in, h_out;
+  StepGraph graph;
+  cudaEvent_t kernels_done = nullptr, copied = nullptr;
+  bool pending = false;
+  // where the results go on wait()
+  int32_t B = 0, n_stride = 0;
+  int32_t* best_idx = nullptr;
+  double* best_cost = nullptr;
+  int32_t* best_meta = nullptr;
+  double* records = nullptr;
+  bool rec_pinned = false;
+  void release() {
+    for (DevBuf* b : {&d_ego, &d_cost, &d_flags, &d_win, &d_records}) b->release();
+    h_in.release();
+    h_out.release();
+    graph.release();
+    if (kernels_done) cudaEventDestroy(kernels_done);
+    if (copied) cudaEventDestroy(copied);
+    kernels_done = copied = nullptr;
+  }
+};
+
 }  // namespace
 
 struct fiss_handle {
@@ -91,10 +174,19 @@ struct fiss_handle {
   // product lattice (fiss_grid): device axes [4][kAxisMax] + the expanded [C][4] table in d_end
   DevBuf d_axes;
   DevBuf d_fit_in, d_fit_out;  // fiss_fit_splines_host / fiss_frame_samples_host
+  cudaStream_t capture_stream = nullptr;       // graph_run: launches are captured here when a graph is (re)built
   cudaStream_t copy_stream = nullptr;          // plan_common: D2H of one half of a big batch under the other half's kernels
   cudaEvent_t part_done[4] = {nullptr, nullptr, nullptr, nullptr};
   std::vector<double> axes_cache;
   int grid_n_max = 0;
+  // kernel launches are collected here instead of being issued while a plan step is being turned into a graph
+  std::vector<KernelLaunch>* record = nullptr;
+  StepGraph graph_dev, graph_host;  // fiss_plan_grid_dev / the small-batch path of the *_host plan calls
+  Lane lanes[kLanes];               // fiss_plan_grid_submit / fiss_plan_grid_wait
+  DevBuf d_pick;                    // fiss_allreduce_pick: slot table + record exchange buffer
+  void* nccl_lib = nullptr;         // dlopen handle of libnccl
+  void* comm = nullptr;             // ncclComm_t created by fiss_comm_init
+  int comm_rank = 0, comm_size = 1;
   size_t smem_attr[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   // resident CTAs per SM of kernel `which` at (threads, smem): asked from the runtime once per distinct launch shape
   // (the query costs microseconds on the latency path of every plan() call)
@@ -180,6 +272,31 @@ struct LaunchPlan {
   int threads = fiss::kThreads;
 };
 
+// Issue one kernel: on the stream, or -- while a plan step is being recorded for a graph -- into the record.
+int32_t issue(fiss_handle* h, cudaStream_t st, KernelLaunch& kl) {
+  if (h->record) {
+    h->record->push_back(kl);
+    return FISS_OK;
+  }
+  void* params[8];
+  kl.params(params);
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = kl.grid;
+  cfg.blockDim = kl.block;
+  cfg.dynamicSmemBytes = kl.smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr{};
+  if (kl.pdl) {  // programmatic dependent launch behind the kernel that produces this one's inputs
+    attr.id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr.val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = &attr;
+    cfg.numAttrs = 1;
+  }
+  FISS_CUDA(h, cudaLaunchKernelExC(&cfg, kl.func, params));
+  h->launches++;
+  return FISS_OK;
+}
+
 template <bool kMat, bool kRec>
 int32_t launch_eval(fiss_handle* h, cudaStream_t st, LaunchPlan& lp, int which) {
   auto kern = fiss::fiss_eval_kernel<kMat, kRec>;
@@ -192,25 +309,14 @@ int32_t launch_eval(fiss_handle* h, cudaStream_t st, LaunchPlan& lp, int which) 
   const int warps = lp.threads / 32;
   const int64_t need = (lp.a.total + warps - 1) / warps;
   lp.grid = (int)std::max<int64_t>(1, std::min<int64_t>(need, (int64_t)h->sm_count * occ));
-  if (lp.a.after_producer) {  // programmatic dependent launch behind the kernel that produces pick_cost / pick_flags
-    cudaLaunchConfig_t cfg{};
-    cfg.gridDim = dim3((unsigned)lp.grid);
-    cfg.blockDim = dim3((unsigned)lp.threads);
-    cfg.dynamicSmemBytes = lp.smem;
-    cfg.stream = st;
-    cudaLaunchAttribute attr{};
-    attr.id = cudaLaunchAttributeProgrammaticStreamSerialization;
-    attr.val.programmaticStreamSerializationAllowed = 1;
-    cfg.attrs = &attr;
-    cfg.numAttrs = 1;
-    FISS_CUDA(h, cudaLaunchKernelEx(&cfg, kern, lp.a));
-    h->launches++;
-    return FISS_OK;
-  }
-  kern<<<lp.grid, lp.threads, lp.smem, st>>>(lp.a);
-  h->launches++;
-  FISS_CUDA(h, cudaGetLastError());
-  return FISS_OK;
+  KernelLaunch kl;
+  kl.func = (const void*)kern;
+  kl.grid = dim3((unsigned)lp.grid);
+  kl.block = dim3((unsigned)lp.threads);
+  kl.smem = lp.smem;
+  kl.pdl = lp.a.after_producer != 0;
+  kl.push(lp.a);
+  return issue(h, st, kl);
 }
 
 // Fill everything of EvalArgs that depends on the scene and on the step bound `n_bound`.
@@ -249,6 +355,131 @@ int32_t plan_launch(fiss_handle* h, const fiss_params* p, int64_t total, int n_b
   lp.smem = base + (a.obs_in_smem ? obs_bytes : 0);
   if (lp.smem > kSmemLimit)
     return fail(h, FISS_ERR_CAPACITY, "spline table + per-warp scratch exceed 227 KB of shared memory");
+  return FISS_OK;
+}
+
+// Run a recorded plan step as a graph (see StepGraph).  `kl` is what the planning code just recorded.
+bool graphs_enabled() {
+  static const bool off = std::getenv("FISS_NO_GRAPH") != nullptr;  // A/B switch: issue the launches one by one
+  return !off;
+}
+
+int32_t graph_build_by_capture(fiss_handle* h, StepGraph& G, std::vector<KernelLaunch>& kl) {
+  // The launches are captured on a private stream (the caller's may be the legacy default stream, which cannot be
+  // captured): a launch with the programmatic-serialisation attribute is recorded as a programmatic edge by the runtime.
+  if (!h->capture_stream) FISS_CUDA(h, cudaStreamCreateWithFlags(&h->capture_stream, cudaStreamNonBlocking));
+  FISS_CUDA(h, cudaStreamBeginCapture(h->capture_stream, cudaStreamCaptureModeThreadLocal));
+  int32_t rc_cap = FISS_OK;
+  const int64_t launches_before = h->launches;
+  for (size_t i = 0; i < kl.size() && rc_cap == FISS_OK; ++i) rc_cap = issue(h, h->capture_stream, kl[i]);
+  h->launches = launches_before;
+  cudaError_t e_end = cudaStreamEndCapture(h->capture_stream, &G.graph);
+  if (rc_cap != FISS_OK) return rc_cap;
+  FISS_CUDA(h, e_end);
+  size_t n_nodes = 0;
+  FISS_CUDA(h, cudaGraphGetNodes(G.graph, nullptr, &n_nodes));
+  std::vector<cudaGraphNode_t> nodes(n_nodes);
+  FISS_CUDA(h, cudaGraphGetNodes(G.graph, nodes.data(), &n_nodes));
+  G.knodes.assign(kl.size(), nullptr);
+  for (cudaGraphNode_t n : nodes) {
+    cudaGraphNodeType ty;
+    FISS_CUDA(h, cudaGraphNodeGetType(n, &ty));
+    if (ty != cudaGraphNodeTypeKernel) continue;
+    cudaKernelNodeParams kp{};
+    FISS_CUDA(h, cudaGraphKernelNodeGetParams(n, &kp));
+    for (size_t i = 0; i < kl.size(); ++i)
+      if (!G.knodes[i] && kp.func == kl[i].func) {
+        G.knodes[i] = n;
+        break;
+      }
+  }
+  for (cudaGraphNode_t n : G.knodes)
+    if (!n) return fail(h, FISS_ERR_CUDA, "graph capture: a kernel node was not found");
+  return FISS_OK;
+}
+
+int32_t graph_build_explicit(fiss_handle* h, StepGraph& G, std::vector<KernelLaunch>& kl, const void* h2d_src, void* h2d_dst,
+                             size_t h2d_bytes, const void* d2h_src, void* d2h_dst, size_t d2h_bytes) {
+  FISS_CUDA(h, cudaGraphCreate(&G.graph, 0));
+  cudaGraphNode_t prev = nullptr;
+  if (h2d_bytes) {
+    cudaGraphNode_t n;
+    FISS_CUDA(h, cudaGraphAddMemcpyNode1D(&n, G.graph, nullptr, 0, h2d_dst, h2d_src, h2d_bytes, cudaMemcpyHostToDevice));
+    prev = n;
+  }
+  for (size_t i = 0; i < kl.size(); ++i) {
+    void* params[8];
+    kl[i].params(params);
+    cudaKernelNodeParams kp{};
+    kp.func = const_cast<void*>(kl[i].func);
+    kp.gridDim = kl[i].grid;
+    kp.blockDim = kl[i].block;
+    kp.sharedMemBytes = (unsigned)kl[i].smem;
+    kp.kernelParams = params;
+    cudaGraphNode_t n;
+    static const bool no_pdl_edge = std::getenv("FISS_GRAPH_NO_PDL") != nullptr;
+    if (kl[i].pdl && prev && i > 0 && !no_pdl_edge) {
+      // programmatic edge from the producer kernel: this kernel may start (and stage its tables) once every CTA of
+      // the producer has signalled griddepcontrol.launch_dependents; it waits for the producer's data itself
+      FISS_CUDA(h, cudaGraphAddKernelNode(&n, G.graph, nullptr, 0, &kp));
+      cudaGraphEdgeData ed{};
+      ed.from_port = cudaGraphKernelNodePortProgrammatic;
+      ed.to_port = 0;
+      ed.type = cudaGraphDependencyTypeProgrammatic;
+      FISS_CUDA(h, cudaGraphAddDependencies_v2(G.graph, &prev, &n, &ed, 1));
+    } else {
+      FISS_CUDA(h, cudaGraphAddKernelNode(&n, G.graph, prev ? &prev : nullptr, prev ? 1 : 0, &kp));
+    }
+    G.knodes.push_back(n);
+    prev = n;
+  }
+  if (d2h_bytes) {
+    cudaGraphNode_t n;
+    FISS_CUDA(h, cudaGraphAddMemcpyNode1D(&n, G.graph, prev ? &prev : nullptr, prev ? 1 : 0, d2h_dst, d2h_src, d2h_bytes,
+                                          cudaMemcpyDeviceToHost));
+  }
+  return FISS_OK;
+}
+
+int32_t graph_run(fiss_handle* h, cudaStream_t st, StepGraph& G, std::vector<KernelLaunch>& kl, const void* h2d_src,
+                  void* h2d_dst, size_t h2d_bytes, const void* d2h_src, void* d2h_dst, size_t d2h_bytes) {
+  bool same = G.exec != nullptr && G.kl.size() == kl.size() && G.h2d_src == h2d_src && G.h2d_dst == h2d_dst &&
+              G.h2d_bytes == h2d_bytes && G.d2h_src == d2h_src && G.d2h_dst == d2h_dst && G.d2h_bytes == d2h_bytes;
+  for (size_t i = 0; same && i < kl.size(); ++i) same = G.kl[i].func == kl[i].func && G.kl[i].pdl == kl[i].pdl;
+  if (!same) {
+    G.release();
+    static const bool by_capture = std::getenv("FISS_GRAPH_CAPTURE") != nullptr;
+    int32_t rc = (by_capture && !h2d_bytes && !d2h_bytes)
+                     ? graph_build_by_capture(h, G, kl)
+                     : graph_build_explicit(h, G, kl, h2d_src, h2d_dst, h2d_bytes, d2h_src, d2h_dst, d2h_bytes);
+    if (rc != FISS_OK) {
+      G.release();
+      return rc;
+    }
+    FISS_CUDA(h, cudaGraphInstantiate(&G.exec, G.graph, 0));
+    G.kl = kl;
+    G.h2d_src = h2d_src; G.h2d_dst = h2d_dst; G.h2d_bytes = h2d_bytes;
+    G.d2h_src = d2h_src; G.d2h_dst = d2h_dst; G.d2h_bytes = d2h_bytes;
+    G.rebuilds++;
+  } else {
+    for (size_t i = 0; i < kl.size(); ++i) {
+      if (G.kl[i].same_shape(kl[i]) && G.kl[i].same_args(kl[i])) continue;
+      void* params[8];
+      kl[i].params(params);
+      cudaKernelNodeParams kp{};
+      kp.func = const_cast<void*>(kl[i].func);
+      kp.gridDim = kl[i].grid;
+      kp.blockDim = kl[i].block;
+      kp.sharedMemBytes = (unsigned)kl[i].smem;
+      kp.kernelParams = params;
+      FISS_CUDA(h, cudaGraphExecKernelNodeSetParams(G.exec, G.knodes[i], &kp));
+      G.kl[i] = kl[i];
+      G.patches++;
+    }
+  }
+  FISS_CUDA(h, cudaGraphLaunch(G.exec, st));
+  G.launches++;
+  h->launches += (int64_t)kl.size();
   return FISS_OK;
 }
 
@@ -326,10 +557,13 @@ int32_t launch_grid(fiss_handle* h, cudaStream_t st, const fiss::GridArgs& a, si
   int occ = 1;
   FISS_CUDA(h, h->occupancy(which, kern, threads, smem, &occ));
   const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(a.items, (int64_t)h->sm_count * occ));
-  kern<<<grid, threads, smem, st>>>(a);
-  h->launches++;
-  FISS_CUDA(h, cudaGetLastError());
-  return FISS_OK;
+  KernelLaunch kl;
+  kl.func = (const void*)kern;
+  kl.grid = dim3((unsigned)grid);
+  kl.block = dim3((unsigned)threads);
+  kl.smem = smem;
+  kl.push(a);
+  return issue(h, st, kl);
 }
 
 int32_t eval_grid(fiss_handle* h, cudaStream_t st, const double* d_ego, int B, const fiss_grid* g, int n_max,
@@ -486,7 +720,12 @@ int32_t fiss_destroy(fiss_handle* h) {
     b->release();
   h->h_in.release();
   h->h_out.release();
+  h->graph_dev.release();
+  h->graph_host.release();
+  h->d_pick.release();
+  for (auto& ln : h->lanes) ln.release();
   if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
+  if (h->capture_stream) cudaStreamDestroy(h->capture_stream);
   for (auto& ev : h->part_done)
     if (ev) cudaEventDestroy(ev);
   delete h;
@@ -778,9 +1017,19 @@ int32_t fiss_pick_winners_dev(fiss_handle* h, void* stream, const double* d_ego,
   FISS_ON_DEVICE(h);
   cudaStream_t st = (cudaStream_t)stream;
   if (!d_records) {
-    fiss::fiss_pick_kernel<<<B, fiss::kPickThreads, 0, st>>>(d_cost, d_flags, C, d_best_idx, d_best_cost, d_end, d_best_meta);
-    h->launches++;
-    FISS_CUDA(h, cudaGetLastError());
+    KernelLaunch kl;
+    kl.func = (const void*)fiss::fiss_pick_kernel;
+    kl.grid = dim3((unsigned)B);
+    kl.block = dim3((unsigned)fiss::kPickThreads);
+    kl.push(d_cost);
+    kl.push(d_flags);
+    kl.push((int)C);
+    kl.push(d_best_idx);
+    kl.push(d_best_cost);
+    kl.push(d_end);
+    kl.push(d_best_meta);
+    rc = issue(h, st, kl);
+    if (rc != FISS_OK) return rc;
   } else {  // one launch: the record kernel's warp of problem b picks b's winner first
     LaunchPlan lp{};
     rc = plan_launch(h, p, B, n_stride, lp);
@@ -857,26 +1106,35 @@ static int32_t plan_common(fiss_handle* h, cudaStream_t st, const double* ego, i
       FISS_CUDA(h, h->h_in.ensure((size_t)B * 48));
       char* da = h->d_arena.as<char>();
       char* ha = h->h_out.as<char>();
-      const void* src = ego;
-      if (!host_is_pinned(ego)) {
-        std::memcpy(h->h_in.p, ego, (size_t)B * 48);
-        src = h->h_in.p;
-      }
-      FISS_CUDA(h, cudaMemcpyAsync(h->d_ego.p, src, (size_t)B * 48, cudaMemcpyHostToDevice, st));
+      const bool as_graph = graphs_enabled();
+      // a few hundred bytes: staged through the handle's pinned block (asking the runtime whether the caller's pointer
+      // is page-locked costs more than the copy)
+      std::memcpy(h->h_in.p, ego, (size_t)B * 48);
       const double* ego_p = h->d_ego.as<double>();
       double* cost_p = cost ? reinterpret_cast<double*>(da + a_vol) : h->d_cost.as<double>();
       uint32_t* flags_p = flags ? reinterpret_cast<uint32_t*>(da + a_flags) : h->d_flags.as<uint32_t>();
+      // the two kernels of the cycle -- lattice kernel, pick + record kernel behind a programmatic edge -- are ONE graph
+      // launch; the two small copies stay ordinary stream copies (measured on the B200: as memcpy
+      // NODES of the graph they cost 6 us more per cycle than cudaMemcpyAsync)
+      std::vector<KernelLaunch> kl;
+      FISS_CUDA(h, cudaMemcpyAsync(h->d_ego.p, h->h_in.p, (size_t)B * 48, cudaMemcpyHostToDevice, st));
+      if (as_graph) h->record = &kl;
       if (g) {
         rc = eval_grid(h, st, ego_p, B, g, n_max, p, cost_p, flags_p, nullptr, n_stride);
       } else {
         rc = fiss_eval_candidates_dev(h, stream, ego_p, B, h->d_end.as<double>(), C, p, cost_p, flags_p, nullptr, n_stride);
       }
+      if (rc == FISS_OK)
+        rc = fiss_pick_winners_dev(h, stream, ego_p, B, h->d_end.as<double>(), C, p, cost_p, flags_p,
+                                   reinterpret_cast<int32_t*>(da + w_idx), reinterpret_cast<double*>(da + w_cost),
+                                   records ? reinterpret_cast<double*>(da + a_rec) : nullptr,
+                                   reinterpret_cast<int32_t*>(da + w_meta), n_stride);
+      h->record = nullptr;
       if (rc != FISS_OK) return rc;
-      rc = fiss_pick_winners_dev(h, stream, ego_p, B, h->d_end.as<double>(), C, p, cost_p, flags_p,
-                                 reinterpret_cast<int32_t*>(da + w_idx), reinterpret_cast<double*>(da + w_cost),
-                                 records ? reinterpret_cast<double*>(da + a_rec) : nullptr,
-                                 reinterpret_cast<int32_t*>(da + w_meta), n_stride);
-      if (rc != FISS_OK) return rc;
+      if (as_graph) {
+        rc = graph_run(h, st, h->graph_host, kl, nullptr, nullptr, 0, nullptr, nullptr, 0);
+        if (rc != FISS_OK) return rc;
+      }
       FISS_CUDA(h, cudaMemcpyAsync(ha, da, a_end, cudaMemcpyDeviceToHost, st));
       FISS_CUDA(h, cudaStreamSynchronize(st));
       std::memcpy(best_cost, ha + w_cost, (size_t)B * 8);
@@ -1029,6 +1287,128 @@ int32_t fiss_plan_grid_host(fiss_handle* h, void* stream, const double* ego, int
   if (n_stride < n_max) return fail(h, FISS_ERR_INVALID, "n_stride is smaller than a candidate's step count");
   const int C = g->nd * g->nv * g->nt;
   return plan_common(h, st, ego, B, C, g, n_max, p, best_idx, best_cost, best_meta, records, n_stride, cost, flags);
+}
+
+int32_t fiss_plan_grid_dev(fiss_handle* h, void* stream, const double* d_ego, int32_t B, const fiss_grid* g,
+                           const fiss_params* p, double* d_cost, uint32_t* d_flags, double* d_mat, int32_t* d_best_idx,
+                           double* d_best_cost, int32_t* d_best_meta, double* d_records, int32_t n_stride) {
+  if (!h) return FISS_ERR_INVALID;
+  if (!d_ego || !d_cost || !d_flags || !d_best_idx || !d_best_cost || B < 1)
+    return fail(h, FISS_ERR_INVALID, "plan_grid_dev: bad arguments");
+  int32_t rc = check_params(h, p);
+  if (rc != FISS_OK) return rc;
+  FISS_ON_DEVICE(h);
+  cudaStream_t st = (cudaStream_t)stream;
+  int n_max = 0;
+  rc = ensure_grid(h, st, g, p, &n_max);
+  if (rc != FISS_OK) return rc;
+  const int C = g->nd * g->nv * g->nt;
+  const bool as_graph = graphs_enabled();
+  std::vector<KernelLaunch> kl;
+  if (as_graph) h->record = &kl;
+  rc = eval_grid(h, st, d_ego, B, g, n_max, p, d_cost, d_flags, d_mat, n_stride);
+  if (rc == FISS_OK)
+    rc = fiss_pick_winners_dev(h, stream, d_ego, B, h->d_end.as<double>(), C, p, d_cost, d_flags, d_best_idx, d_best_cost,
+                               d_records, d_best_meta, n_stride);
+  h->record = nullptr;
+  if (rc != FISS_OK || !as_graph) return rc;
+  return graph_run(h, st, h->graph_dev, kl, nullptr, nullptr, 0, nullptr, nullptr, 0);
+}
+
+int32_t fiss_plan_grid_submit(fiss_handle* h, void* stream, int32_t lane, const double* ego, int32_t B, const fiss_grid* g,
+                              const fiss_params* p, int32_t* best_idx, double* best_cost, int32_t* best_meta,
+                              double* records, int32_t n_stride) {
+  if (!h) return FISS_ERR_INVALID;
+  if (lane < 0 || lane >= kLanes) return fail(h, FISS_ERR_INVALID, "plan_grid_submit: lane must be 0 or 1");
+  if (!ego || !best_idx || !best_cost || B < 1) return fail(h, FISS_ERR_INVALID, "plan_grid_submit: bad arguments");
+  Lane& ln = h->lanes[lane];
+  if (ln.pending) return fail(h, FISS_ERR_STATE, "plan_grid_submit: the lane still has a call in flight (fiss_plan_grid_wait it first)");
+  int32_t rc = check_params(h, p);
+  if (rc != FISS_OK) return rc;
+  FISS_ON_DEVICE(h);
+  cudaStream_t st = (cudaStream_t)stream;
+  int n_max = 0;
+  rc = ensure_grid(h, st, g, p, &n_max);
+  if (rc != FISS_OK) return rc;
+  if (n_stride < n_max) return fail(h, FISS_ERR_INVALID, "n_stride is smaller than a candidate's step count");
+  if (!h->copy_stream) {
+    FISS_CUDA(h, cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
+    for (auto& ev : h->part_done) FISS_CUDA(h, cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+  }
+  if (!ln.kernels_done) {
+    FISS_CUDA(h, cudaEventCreateWithFlags(&ln.kernels_done, cudaEventDisableTiming));
+    FISS_CUDA(h, cudaEventCreateWithFlags(&ln.copied, cudaEventDisableTiming));
+  }
+  const int C = g->nd * g->nv * g->nt;
+  const size_t total = (size_t)B * C, rec_doubles = records ? (size_t)B * FISS_REC_ROWS * n_stride : 0;
+  const size_t w_cost = 0, w_meta = (size_t)B * 8, w_idx = (size_t)B * 16, w_bytes = (size_t)B * 20;
+  FISS_CUDA(h, ln.d_ego.ensure((size_t)B * 48));
+  FISS_CUDA(h, ln.d_cost.ensure(total * 8));
+  FISS_CUDA(h, ln.d_flags.ensure(total * 4));
+  FISS_CUDA(h, ln.d_win.ensure(w_bytes));
+  if (records) FISS_CUDA(h, ln.d_records.ensure(rec_doubles * 8));
+  const bool pin_rec = host_is_pinned(records);
+  const size_t o_rec = (w_bytes + 15) & ~(size_t)15;
+  FISS_CUDA(h, ln.h_out.ensure(o_rec + (pin_rec ? 0 : rec_doubles * 8)));
+  FISS_CUDA(h, ln.h_in.ensure((size_t)B * 48));
+  const bool as_graph = graphs_enabled();
+  const void* src = ego;
+  if (!host_is_pinned(ego)) {
+    std::memcpy(ln.h_in.p, ego, (size_t)B * 48);
+    src = ln.h_in.p;
+  }
+  char* dw = ln.d_win.as<char>();
+  std::vector<KernelLaunch> kl;
+  FISS_CUDA(h, cudaMemcpyAsync(ln.d_ego.p, src, (size_t)B * 48, cudaMemcpyHostToDevice, st));
+  if (as_graph) h->record = &kl;
+  rc = eval_grid(h, st, ln.d_ego.as<double>(), B, g, n_max, p, ln.d_cost.as<double>(), ln.d_flags.as<uint32_t>(), nullptr, n_stride);
+  if (rc == FISS_OK)
+    rc = fiss_pick_winners_dev(h, stream, ln.d_ego.as<double>(), B, h->d_end.as<double>(), C, p, ln.d_cost.as<double>(),
+                               ln.d_flags.as<uint32_t>(), reinterpret_cast<int32_t*>(dw + w_idx),
+                               reinterpret_cast<double*>(dw + w_cost), records ? ln.d_records.as<double>() : nullptr,
+                               reinterpret_cast<int32_t*>(dw + w_meta), n_stride);
+  h->record = nullptr;
+  if (rc != FISS_OK) return rc;
+  if (as_graph) {
+    rc = graph_run(h, st, ln.graph, kl, nullptr, nullptr, 0, nullptr, nullptr, 0);
+    if (rc != FISS_OK) return rc;
+  }
+  // the copy-back runs on the handle's second stream: the kernels of the next submit (other lane) execute under it
+  FISS_CUDA(h, cudaEventRecord(ln.kernels_done, st));
+  FISS_CUDA(h, cudaStreamWaitEvent(h->copy_stream, ln.kernels_done, 0));
+  char* ho = ln.h_out.as<char>();
+  FISS_CUDA(h, cudaMemcpyAsync(ho, dw, w_bytes, cudaMemcpyDeviceToHost, h->copy_stream));
+  if (records)
+    FISS_CUDA(h, cudaMemcpyAsync(pin_rec ? (void*)records : (void*)(ho + o_rec), ln.d_records.p, rec_doubles * 8,
+                                 cudaMemcpyDeviceToHost, h->copy_stream));
+  FISS_CUDA(h, cudaEventRecord(ln.copied, h->copy_stream));
+  ln.pending = true;
+  ln.B = B;
+  ln.n_stride = n_stride;
+  ln.best_idx = best_idx;
+  ln.best_cost = best_cost;
+  ln.best_meta = best_meta;
+  ln.records = records;
+  ln.rec_pinned = pin_rec;
+  return FISS_OK;
+}
+
+int32_t fiss_plan_grid_wait(fiss_handle* h, int32_t lane) {
+  if (!h) return FISS_ERR_INVALID;
+  if (lane < 0 || lane >= kLanes) return fail(h, FISS_ERR_INVALID, "plan_grid_wait: lane must be 0 or 1");
+  Lane& ln = h->lanes[lane];
+  if (!ln.pending) return fail(h, FISS_ERR_STATE, "plan_grid_wait: nothing in flight on this lane");
+  FISS_ON_DEVICE(h);
+  ln.pending = false;
+  FISS_CUDA(h, cudaEventSynchronize(ln.copied));
+  const size_t B = (size_t)ln.B, w_cost = 0, w_meta = B * 8, w_idx = B * 16, w_bytes = B * 20;
+  const char* ho = ln.h_out.as<char>();
+  std::memcpy(ln.best_cost, ho + w_cost, B * 8);
+  std::memcpy(ln.best_idx, ho + w_idx, B * 4);
+  if (ln.best_meta) std::memcpy(ln.best_meta, ho + w_meta, B * 8);
+  if (ln.records && !ln.rec_pinned)
+    std::memcpy(ln.records, ho + ((w_bytes + 15) & ~(size_t)15), B * FISS_REC_ROWS * ln.n_stride * 8);
+  return FISS_OK;
 }
 
 int32_t fiss_eval_end_states_host(fiss_handle* h, void* stream, const double* ego6, const double* end, int32_t N,

@@ -142,6 +142,8 @@ class FissEngine:
         # (or a planner and its lazy candidate bundles) sharing one engine can tell that the tables are no longer theirs
         self.spline_token = 0
         self.obstacle_token = 0
+        self._ego_stage = np.zeros((self._STAGE_ROWS, 6), np.float64)
+        self._ego_stage_ptr = _shim.ptr(self._ego_stage)
 
     # ------------------------------------------------------------------ plumbing
     def close(self):
@@ -272,24 +274,56 @@ class FissEngine:
                     cost=mk((b, c), np.float64) if want_volume else None,
                     flags=mk((b, c), np.uint32) if want_volume else None)
 
+    _OUT_KEYS = ("best_idx", "best_cost", "meta", "records", "cost", "flags")
+    _STAGE_ROWS = 64
+
+    def _out_ptrs(self, out: dict):
+        """ctypes pointers of an output set, made once (``ndarray.ctypes`` costs microseconds per array -- more than the
+        rest of the call's host side); kept in the dict under ``"_ptrs"``."""
+        ptrs = out.get("_ptrs")
+        if ptrs is None:
+            ptrs = tuple(_shim.ptr(out[k]) for k in self._OUT_KEYS)
+            out["_ptrs"] = ptrs
+        return ptrs
+
     def plan_grid(self, ego: np.ndarray, grid: LatticeGrid, params: FissParams, want_records: bool = True,
                   want_volume: bool = False, stream=None, out: dict = None) -> dict:
         """plan() for ``ego [B, 6]`` over a product lattice (the lattice kernel).  ``out`` (from
         ``alloc_plan_outputs``) is filled in place and returned: no allocation on the call path, and pinned
         buffers -- ``ego`` included -- are the DMA endpoints themselves."""
-        if not (isinstance(ego, np.ndarray) and ego.ndim == 2 and ego.dtype == np.float64 and ego.flags.c_contiguous):
-            ego = np.ascontiguousarray(np.atleast_2d(ego), dtype=np.float64)
-        b, c = ego.shape[0], grid.num_candidates
+        b = 1 if getattr(ego, "ndim", 2) == 1 else len(ego)
+        if b <= self._STAGE_ROWS:
+            # small batches (the plan-cycle latency path): into the engine's own staging rows, whose pointer is cached
+            self._ego_stage[:b] = ego
+            ego_ptr = self._ego_stage_ptr
+        else:
+            if not (isinstance(ego, np.ndarray) and ego.ndim == 2 and ego.dtype == np.float64 and ego.flags.c_contiguous):
+                ego = np.ascontiguousarray(np.atleast_2d(ego), dtype=np.float64)
+            ego_ptr = _shim.ptr(ego)
         n_stride = grid.n_stride
         if out is None:
             out = self.alloc_plan_outputs(b, grid, want_records, want_volume, pinned=False)
         else:
             assert out["best_idx"].shape == (b,) and (out["records"] is None or out["records"].shape[2] == n_stride)
-        self._check(self._lib.fiss_plan_grid_host(
-            self._h, self._stream(stream), _shim.ptr(ego), b, C.byref(grid.c_struct), C.byref(params),
-            _shim.ptr(out["best_idx"]), _shim.ptr(out["best_cost"]), _shim.ptr(out["meta"]), _shim.ptr(out["records"]),
-            n_stride, _shim.ptr(out["cost"]), _shim.ptr(out["flags"])), "fiss_plan_grid_host")
+        p = self._out_ptrs(out)
+        rc = self._lib.fiss_plan_grid_host(self._h, self._stream(stream), ego_ptr, b, C.byref(grid.c_struct), C.byref(params),
+                                           p[0], p[1], p[2], p[3], n_stride, p[4], p[5])
+        if rc != _shim.FISS_OK:
+            self._check(rc, "fiss_plan_grid_host")
         return out
+
+    def plan_grid_submit(self, lane: int, ego: np.ndarray, grid: LatticeGrid, params: FissParams, out: dict, stream=None):
+        """Streaming ``plan_grid``: enqueue batch ``ego [B, 6]`` on ``lane`` (0 / 1) and return at once; the results land
+        in ``out`` (from ``alloc_plan_outputs(..., want_volume=False)``) when ``plan_grid_wait(lane)`` returns.  The
+        copy-back of one lane overlaps the kernels of the other."""
+        assert isinstance(ego, np.ndarray) and ego.ndim == 2 and ego.dtype == np.float64 and ego.flags.c_contiguous
+        p = self._out_ptrs(out)
+        self._check(self._lib.fiss_plan_grid_submit(
+            self._h, self._stream(stream), int(lane), _shim.ptr(ego), ego.shape[0], C.byref(grid.c_struct), C.byref(params),
+            p[0], p[1], p[2], p[3], grid.n_stride), "fiss_plan_grid_submit")
+
+    def plan_grid_wait(self, lane: int):
+        self._check(self._lib.fiss_plan_grid_wait(self._h, int(lane)), "fiss_plan_grid_wait")
 
     def eval_end_states(self, ego6: np.ndarray, end: np.ndarray, params: FissParams, want_records: bool = False,
                         stream=None) -> dict:
@@ -319,6 +353,15 @@ class FissEngine:
             self._h, self._stream(stream), C.c_void_p(ego_t.data_ptr()), ego_t.shape[0], C.byref(grid.c_struct),
             C.byref(params), C.c_void_p(cost_t.data_ptr()), C.c_void_p(flags_t.data_ptr()),
             C.c_void_p(mat_t.data_ptr()) if mat_t is not None else None, int(n_stride)), "fiss_eval_grid_dev")
+
+    def plan_grid_dev(self, ego_t, grid: LatticeGrid, params: FissParams, cost_t, flags_t, mat_t, best_idx_t, best_cost_t,
+                      meta_t, records_t, n_stride: int, stream=None):
+        """One plan step on device buffers (lattice kernel + pick / records) -- one graph launch from the second call on."""
+        vp = lambda t: C.c_void_p(t.data_ptr()) if t is not None else None  # noqa: E731
+        self._check(self._lib.fiss_plan_grid_dev(
+            self._h, self._stream(stream), vp(ego_t), ego_t.shape[0], C.byref(grid.c_struct), C.byref(params), vp(cost_t),
+            vp(flags_t), vp(mat_t), vp(best_idx_t), vp(best_cost_t), vp(meta_t), vp(records_t), int(n_stride)),
+            "fiss_plan_grid_dev")
 
     def pick_winners_dev(self, ego_t, end_t, params: FissParams, cost_t, flags_t, best_idx_t, best_cost_t,
                          records_t, meta_t, n_stride: int, stream=None):

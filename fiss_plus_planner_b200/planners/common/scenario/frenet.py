@@ -177,16 +177,16 @@ class FrenetTrajectory(object):
         ragged lengths: ``ds, c`` n'-1, ``c_d`` n'-2, ``c_dd`` n'-3; for n' < 2 they stay empty
         (frenet_optimal_planner.py:121-134).
         """
-        for row, name in enumerate(RECORD_FIELDS[:9]):
-            setattr(self, name, rec[row, :n].copy())
-        self.x = rec[9, :n_cart].copy()
-        self.y = rec[10, :n_cart].copy()
+        rec = rec.copy()            # ONE private copy; the fields are views into it (the caller's buffer is reused)
+        (self.t, self.s, self.s_d, self.s_dd, self.s_ddd, self.d, self.d_d, self.d_dd, self.d_ddd) = rec[:9, :n]
+        self.x = rec[9, :n_cart]
+        self.y = rec[10, :n_cart]
         if n_cart >= 2:
-            self.yaw = rec[11, :n_cart].copy()
-            self.ds = rec[12, :n_cart - 1].copy()
-            self.c = rec[13, :n_cart - 1].copy()
-            self.c_d = rec[14, :max(n_cart - 2, 0)].copy()
-            self.c_dd = rec[15, :max(n_cart - 3, 0)].copy()
+            self.yaw = rec[11, :n_cart]
+            self.ds = rec[12, :n_cart - 1]
+            self.c = rec[13, :n_cart - 1]
+            self.c_d = rec[14, :max(n_cart - 2, 0)]
+            self.c_dd = rec[15, :max(n_cart - 3, 0)]
         else:
             self.yaw, self.ds, self.c, self.c_d, self.c_dd = [], [], [], [], []
         self.cost_final = cost

@@ -135,7 +135,8 @@ class FissPlanner(FrenetOptimalPlanner):
     def _evaluate_grid(self, time_step_now: int):
         """The one launch per cycle: cost + masks of every lattice point."""
         self._prm = self._params(time_step_now)
-        out = self.engine.plan_grid(self._ego6[None], self._fgrid, self._prm, want_records=False, want_volume=True)
+        out = self.engine.plan_grid(self._ego6, self._fgrid, self._prm, want_records=False, want_volume=True,
+                                    out=self._plan_outputs(self._fgrid, want_records=False))
         self._cost, self._flags = out["cost"][0], out["flags"][0]
 
     # -- lazy generation (bookkeeping only; the numbers are already on the host) ---------------------

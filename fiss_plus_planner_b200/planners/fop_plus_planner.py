@@ -45,7 +45,8 @@ class FopPlusPlanner(FrenetOptimalPlanner):
         end = self._end_states()
         prm = self._params(time_step_now)
         ego6 = frenet_state.as_ego6()
-        out = self.engine.plan_grid(ego6[None], self._lattice_grid(), prm, want_records=True, want_volume=True)
+        grid = self._lattice_grid()
+        out = self.engine.plan_grid(ego6, grid, prm, want_records=True, want_volume=True, out=self._plan_outputs(grid))
         cost, flags = out["cost"][0], out["flags"][0]
         self.stats.num_trajs_generated = len(end)
         self.all_trajs.append(self._bundle(ego6, end, prm, cost, flags))

@@ -203,6 +203,11 @@ class FrenetOptimalPlanner(object):
         self._lattice_key = None
         self._lattice = None
         self._grid = None
+        self._params_key = None
+        self._params_proto = None
+        self._out = None
+        self._out_key = None
+        self._out_grid = None
         self.check_curvature = False  # optional third mask bit; off = reference behaviour (:145-150)
 
     # -- device plumbing -------------------------------------------------------------------------
@@ -271,8 +276,28 @@ class FrenetOptimalPlanner(object):
         return self._grid
 
     def _params(self, time_step_now: int, collide_all: bool = False):
-        return make_params(self.settings, self.vehicle, self.cost_function.as_device_weights(), time_step_now,
-                           check_res=2, check_curvature=self.check_curvature, collide_all=collide_all)
+        """``struct fiss_params`` of this cycle.  Building the 16-field ctypes struct costs several microseconds -- a tenth
+        of a plan cycle --, so it is rebuilt only when a setting, a vehicle limit or a switch changed; a cycle gets its
+        own copy (the candidate bundles keep theirs) with ``time_step_now`` filled in."""
+        st, veh = self.settings, self.vehicle
+        key = (st.tick_t, st.highest_speed, veh.max_speed, veh.max_accel, getattr(veh, "max_curvature", None), veh.l, veh.w,
+               self.check_curvature, collide_all)
+        if key != self._params_key:
+            self._params_proto = make_params(st, veh, self.cost_function.as_device_weights(), 0, check_res=2,
+                                             check_curvature=self.check_curvature, collide_all=collide_all)
+            self._params_key = key
+        prm = type(self._params_proto).from_buffer_copy(self._params_proto)
+        prm.time_step_now = int(time_step_now)
+        return prm
+
+    def _plan_outputs(self, grid, batch: int = 1, want_records: bool = True) -> dict:
+        """The planner's reusable output set for ``plan_grid`` (winners, records, cost / flags volume): allocating six
+        arrays and taking their addresses every cycle cost more host time than the call itself."""
+        if self._out is None or self._out_key != (id(grid), batch, want_records):
+            self._out = self.engine.alloc_plan_outputs(batch, grid, want_records=want_records, want_volume=True, pinned=False)
+            self._out_key = (id(grid), batch, want_records)
+            self._out_grid = grid           # keeps id(grid) alive
+        return self._out
 
     def _trajectory_from_record(self, rec, meta, cost) -> FrenetTrajectory:
         return FrenetTrajectory().fill_from_device_record(rec, int(meta[0]), int(meta[1]), float(cost))
@@ -311,7 +336,8 @@ class FrenetOptimalPlanner(object):
         prm = self._params(time_step_now)
         ego6 = frenet_state.as_ego6() if hasattr(frenet_state, "as_ego6") else np.array(
             [frenet_state.s, frenet_state.s_d, frenet_state.s_dd, frenet_state.d, frenet_state.d_d, frenet_state.d_dd])
-        out = self.engine.plan_grid(ego6[None], self._lattice_grid(), prm, want_records=True, want_volume=True)
+        grid = self._lattice_grid()
+        out = self.engine.plan_grid(ego6, grid, prm, want_records=True, want_volume=True, out=self._plan_outputs(grid))
 
         n_cand = len(end)
         self.stats.num_trajs_generated = n_cand

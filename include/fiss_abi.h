@@ -182,6 +182,14 @@ int32_t fiss_full_records_dev(fiss_handle* h, void* stream, const double* d_ego6
                               const int32_t* d_sel, int32_t N, const fiss_params* p,
                               double* d_records, double* d_cost, uint32_t* d_flags, int32_t n_stride);
 
+/* One plan step on caller-owned DEVICE buffers: fiss_eval_grid_dev + fiss_pick_winners_dev (the pick fused into the
+ * record launch when d_records != NULL) as ONE call -- and, from the second call with the same buffers on, as one
+ * cudaGraphLaunch of an instantiated graph whose kernel nodes are patched when the parameters change (time_step_now
+ * moves every cycle, planning.py:124-128).  Asynchronous on `stream`.  d_mat / d_records / d_best_meta may be NULL. */
+int32_t fiss_plan_grid_dev(fiss_handle* h, void* stream, const double* d_ego, int32_t B, const fiss_grid* g,
+                           const fiss_params* p, double* d_cost, uint32_t* d_flags, double* d_mat, int32_t* d_best_idx,
+                           double* d_best_cost, int32_t* d_best_meta, double* d_records, int32_t n_stride);
+
 /* ---- host-pointer API (what the Python planners and a C caller use) ------------------------ */
 /* plan() for B ego states over one shared lattice: H2D of ego/end states, the hot kernel, the pick
  * kernel, D2H of winners -- all inside, synchronous on return.
@@ -196,6 +204,17 @@ int32_t fiss_plan_lattice_host(fiss_handle* h, void* stream, const double* ego, 
 int32_t fiss_plan_grid_host(fiss_handle* h, void* stream, const double* ego, int32_t B, const fiss_grid* g,
                             const fiss_params* p, int32_t* best_idx, double* best_cost, int32_t* best_meta,
                             double* records, int32_t n_stride, double* cost, uint32_t* flags);
+
+/* Streaming twin of fiss_plan_grid_host for a sequence of batches (planning.py:120-128 calls plan() once per step; a
+ * batched caller submits one batch of ego states per step): `submit` enqueues H2D + kernels + D2H of batch k on lane
+ * k % 2 and returns; `wait` blocks until that lane's winners / records are in the caller's buffers.  The device->host
+ * copy of one lane runs on a second stream under the kernels of the other lane.  Buffers as in fiss_plan_grid_host
+ * (no cost / flags volume); they must stay valid until the lane has been waited for.  A lane with a call in flight
+ * refuses another submit (FISS_ERR_STATE). */
+int32_t fiss_plan_grid_submit(fiss_handle* h, void* stream, int32_t lane, const double* ego, int32_t B, const fiss_grid* g,
+                              const fiss_params* p, int32_t* best_idx, double* best_cost, int32_t* best_meta,
+                              double* records, int32_t n_stride);
+int32_t fiss_plan_grid_wait(fiss_handle* h, int32_t lane);
 
 /* "evaluate a list of end states" for one ego state: cost + masks for every entry,
  * and full records when `records` != NULL.  */
