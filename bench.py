@@ -583,6 +583,121 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
+# ------------------------------------------------------------------------------------------------ split lattice
+def run_split_lattice(args):
+    """BASELINE config 5 with few problems: ONE fine lattice (33x17x9 = 5049 candidates x <=100 steps,
+    32 obstacles) per problem, its lateral rows split across the ranks; every step = each rank's slab through the
+    lattice kernel + pick, then ``fiss_allreduce_pick`` (NCCL from the C-ABI: one all-reduce for the pick, one for the
+    winner's record).  STRONG scaling: the problems are the same on every rank, the work per GPU shrinks with N."""
+    import torch
+    import torch.distributed as dist
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    saved_stdout = None
+    if world > 1:
+        sys.stdout.flush()
+        saved_stdout = os.dup(1)
+        os.dup2(2, 1)
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    from fiss_plus_planner_b200 import synthetic as syn
+    from fiss_plus_planner_b200.batch import SplitLatticePlanner
+    from fiss_plus_planner_b200.engine import FissEngine, fop_grid, make_params
+    from fiss_plus_planner_b200.planners.common.cost.cost_function import CostFunction
+    from fiss_plus_planner_b200.planners.common.vehicle.vehicle import Vehicle
+    from fiss_plus_planner_b200.planners.frenet_optimal_planner import FrenetOptimalPlannerSettings
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    B = args.batch_per_gpu
+    sc = syn.make_scene(SCENE, batch=B, num_obstacles=NUM_OBS)
+    veh = Vehicle(syn.vehicle_params())
+    st = FrenetOptimalPlannerSettings(*LATTICE)
+    st.min_t, st.max_t, st.highest_speed = MIN_T, MAX_T, sc.max_target_speed
+    eng = FissEngine(local_rank)
+    eng.set_spline(sc.spline.device_table())
+    eng.set_obstacles(sc.obs.xyth, sc.obs.lw, sc.obs.valid, sc.obs.final_time_step)
+    grid = fop_grid(st, veh.w)
+    prm = make_params(st, veh, CostFunction("WX1").as_device_weights())
+    sp = SplitLatticePlanner(eng, grid, prm)
+    if world > 1:
+        eng.comm_init()
+    ego = np.ascontiguousarray(sc.ego[:B])
+    first = sp.plan(ego)                               # also allocates the device buffers
+    stream = torch.cuda.current_stream()
+    sptr = stream.cuda_stream
+    f64 = torch.float64
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=f64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    if world == 1:
+        sp._device_buffers(B)
+        sp._dev["ego"].copy_(torch.from_numpy(ego))
+    step = lambda: sp.plan_step_dev(stream=sptr)       # noqa: E731
+    for _ in range(args.warmup):
+        step()
+    barrier()
+    launches0 = eng.launch_count
+    marks = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
+    marks[0].record(stream)
+    for i in range(args.steps):
+        step()
+        marks[i + 1].record(stream)
+    barrier()
+    launches = eng.launch_count - launches0
+    total_ms = max_over_ranks(marks[0].elapsed_time(marks[-1]))
+    median_ms = max_over_ranks(float(np.median([marks[i].elapsed_time(marks[i + 1]) for i in range(args.steps)])))
+    # the device-resident path's winners are the synchronous path's
+    assert np.array_equal(sp._dev["idx"].cpu().numpy().astype(np.int64), np.asarray(first["best_idx"]).astype(np.int64))
+    for _ in range(args.warmup):
+        sp.plan(ego)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        out = sp.plan(ego)
+    e2e_s = max_over_ranks(time.perf_counter() - t0)
+    C = grid.num_candidates
+    n_stride = grid.n_stride
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": B * C * args.steps / (total_ms * 1e-3), "unit": UNIT, "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "ms_per_step_median": median_ms,
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "cfg5 split lattice: %d problem(s) x 33x17x9 lattice (5049 candidates) x n<=100 steps x %d "
+                                   "obstacles; the lattice's 33 lateral rows split across %d GPU(s)" % (B, NUM_OBS, world),
+                       "lattice": list(LATTICE), "obstacles": NUM_OBS, "problems": B,
+                       "parallelism": "lateral rows of ONE lattice split across ranks; per step one ncclAllReduce(MIN, u64, "
+                                      "%d B) for the pick + one ncclAllReduce(SUM, u64, %d B) moving the winners' records, "
+                                      "both issued by libfissgpu.so on the kernels' stream" % (
+                                          B * world * 16, B * (16 * n_stride + 1) * 8),
+                       "l2": "winner-only mode: nothing is materialised; inputs stay resident"},
+            "mode": "winner-only lattice kernel per slab + pick + winner records + cross-GPU pick",
+            "e2e": {"value": B * C * args.steps / e2e_s, "unit": UNIT, "h2d_bytes_per_step": B * 48,
+                    "d2h_bytes_per_step": B * (8 + 4 + 8) + B * 16 * n_stride * 8, "ms_per_step": 1e3 * e2e_s / args.steps,
+                    "call": "SplitLatticePlanner.plan(): H2D of the ego states, slab kernels, fiss_allreduce_pick, D2H of the "
+                            "global winners + records, synchronous per step"},
+            "gpu_launches": int(launches), "winner_ids": [int(v) for v in np.asarray(out["best_idx"])[:8]],
+        }
+        if saved_stdout is not None:
+            sys.stdout.flush()
+            os.write(saved_stdout, (json.dumps(line) + "\n").encode())
+        else:
+            print(json.dumps(line))
+    if world > 1:
+        eng.comm_destroy()
+        dist.destroy_process_group()
+
+
 # ------------------------------------------------------------------------------------------------ reference arm
 def run_reference(args):
     """The reference arm: the reference's own CPU implementation of the path on the box's host cores, same config /
@@ -621,15 +736,22 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch-per-gpu", type=int, default=None)
     ap.add_argument("--workload", default="cfg4", choices=sorted(WORKLOADS))
+    ap.add_argument("--split-lattice", action="store_true",
+                    help="side workload (use with --workload cfg5): ONE lattice split across the ranks, cross-GPU pick by "
+                         "fiss_allreduce_pick; --batch-per-gpu = number of problems (the same on every rank; default 8)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-closed-loop", action="store_true", help="skip the config-1 closed-loop latency section")
     ap.add_argument("--cpu-steps", type=int, default=6,
                     help="CPU-baseline sample: steps of one whole plan() per host core (6 x ~2 s = ~12 s of host time)")
     args = ap.parse_args()
+    if args.split_lattice and args.batch_per_gpu is None:
+        args.batch_per_gpu = 8
     args.batch_per_gpu = select_workload(args.workload, args.batch_per_gpu)
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":
         run_reference(args)
+    elif args.split_lattice:
+        run_split_lattice(args)
     else:
         run_ours(args)
 

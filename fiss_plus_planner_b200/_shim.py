@@ -24,6 +24,7 @@ EXPORTS = (
     "fiss_eval_candidates_dev", "fiss_eval_grid_dev", "fiss_pick_winners_dev", "fiss_full_records_dev",
     "fiss_plan_lattice_host", "fiss_plan_grid_host", "fiss_eval_end_states_host", "fiss_launch_count",
     "fiss_plan_grid_dev", "fiss_plan_grid_submit", "fiss_plan_grid_wait",
+    "fiss_comm_unique_id", "fiss_comm_init", "fiss_comm_destroy", "fiss_allreduce_pick",
 )
 
 
@@ -94,6 +95,10 @@ def load():
         "fiss_plan_grid_dev": (i32, [vp, vp, vp, i32, gp, pp, vp, vp, vp, vp, vp, vp, vp, i32]),
         "fiss_plan_grid_submit": (i32, [vp, vp, i32, vp, i32, gp, pp, vp, vp, vp, vp, i32]),
         "fiss_plan_grid_wait": (i32, [vp, i32]),
+        "fiss_comm_unique_id": (i32, [vp, C.c_char_p]),
+        "fiss_comm_init": (i32, [vp, vp, i32, i32, C.c_char_p]),
+        "fiss_comm_destroy": (i32, [vp]),
+        "fiss_allreduce_pick": (i32, [vp, vp, i32, i32, vp, i32, C.c_int64, C.c_int64, C.c_int64, vp, vp, vp, vp, i32]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(lib, name)

@@ -12,11 +12,13 @@ evaluates a slab of lateral rows -- a contiguous candidate-id range in FrenetOpt
 tie rule (``min_cost >= cost`` scan => the LARGEST index among the minima,
 frenet_optimal_planner.py:263-268):
 
-    ``SplitLatticePlanner``   all_reduce(MIN) on the cost, all_reduce(MAX) on "my index if my cost is
-                              the minimum else -1"; the owner of the winner broadcasts its record.
-
-Tensors are device buffers only (NCCL needs them on the GPU); on CPU (gloo) the same reduction code
-runs on host tensors, which is what the world_size-2 tests exercise.
+    ``SplitLatticePlanner``   on GPUs (NCCL): everything stays on the device -- ``fiss_plan_grid_dev`` picks the slab's
+                              winner, ``fiss_allreduce_pick`` (C-ABI, NCCL called from libfissgpu.so on the kernels'
+                              stream) agrees on the global one with ONE all-reduce and moves the winner's record with
+                              a second; a single device->host copy at the end.
+                              On CPU (gloo; the world_size-2 tests) the same rule runs on host tensors:
+                              all_reduce(MIN) on the cost, all_reduce(MAX) on "my index if my cost is the minimum
+                              else -1", records summed from their owners.
 """
 from __future__ import annotations
 
@@ -98,37 +100,97 @@ class ShardedBatchPlanner(object):
 
 
 class SplitLatticePlanner(object):
-    """BASELINE config 5 with few problems: the lattice's lateral rows are split across ranks.
+    """BASELINE config 5 with few problems: ONE lattice split across ranks, FrenetOptimalPlanner numbering (``"dtv"``).
 
-    Requires FrenetOptimalPlanner numbering (``order == "dtv"``: d outermost), so a slab of lateral rows
-    [i_lo, i_hi) is the contiguous global id range [i_lo * stride_d, i_hi * stride_d)."""
+    ``axis="t"`` (default) gives rank r a slab of horizons ``T[k_lo:k_hi]``: ALL the per-problem work divides -- the
+    longitudinal rows are per (v, T), the lateral rows per (d, T) -- at the price of balance being bounded by the number
+    of horizons (9 horizons on 8 ranks: 2, 1, 1, ...).  ``axis="d"`` gives a slab of lateral rows (a contiguous global id
+    range): every rank then recomputes all the longitudinal rows, so only the lateral / per-candidate work divides.
+    Local candidate ids map to global ones by ``(c // inner) * outer + c % inner + offset`` (``id_map``)."""
 
-    def __init__(self, engine: FissEngine, grid: LatticeGrid, params, group=None):
-        assert grid.order[0] == "d", "split along the outermost axis: use FrenetOptimalPlanner numbering"
-        self.engine, self.grid, self.params, self.group = engine, grid, params, group
+    def __init__(self, engine: FissEngine, grid: LatticeGrid, params, group=None, axis: str = "t"):
+        assert grid.order == "dtv", "FrenetOptimalPlanner numbering (d outer, T, v inner) is required"
+        assert axis in ("t", "d")
+        self.engine, self.grid, self.params, self.group, self.axis = engine, grid, params, group, axis
         self.world, self.rank = _world(group)
-        self.i_lo, self.i_hi = shard_range(len(grid.d), self.world, self.rank)
-        self.id_offset = self.i_lo * grid.strides[0]
-        self.local_grid = (LatticeGrid(grid.d[self.i_lo:self.i_hi], grid.v, grid.T, grid.tick, grid.order)
-                           if self.i_hi > self.i_lo else None)
+        nd, nv, nt = grid.shape
+        if axis == "d":
+            self.lo, self.hi = shard_range(nd, self.world, self.rank)
+            self.id_map = (1 << 40, 0, self.lo * grid.strides[0])
+            self.local_grid = (LatticeGrid(grid.d[self.lo:self.hi], grid.v, grid.T, grid.tick, grid.order)
+                               if self.hi > self.lo else None)
+        else:
+            self.lo, self.hi = shard_range(nt, self.world, self.rank)
+            self.id_map = ((self.hi - self.lo) * nv if self.hi > self.lo else 1, nt * nv, self.lo * nv)
+            self.local_grid = (LatticeGrid(grid.d, grid.v, grid.T[self.lo:self.hi], grid.tick, grid.order)
+                               if self.hi > self.lo else None)
+        self.id_offset = self.id_map[2]
 
-    def owner_of(self, global_idx: int) -> int:
-        i_d = int(global_idx) // self.grid.strides[0]
-        for r in range(self.world):
-            lo, hi = shard_range(len(self.grid.d), self.world, r)
-            if lo <= i_d < hi:
-                return r
-        raise ValueError(global_idx)
+    def to_global(self, local_idx):
+        """Local candidate ids of this rank's slab -> ids of the full lattice (-1 stays -1)."""
+        c = np.asarray(local_idx).astype(np.int64)
+        inner, outer, offset = self.id_map
+        return np.where(c >= 0, (c // inner) * outer + c % inner + offset, -1)
+
+    # ------------------------------------------------------------------ device path (NCCL inside the C-ABI)
+    def _device_buffers(self, b: int):
+        key = (b, self.grid.n_stride, self.local_grid.num_candidates if self.local_grid is not None else 0)
+        if getattr(self, "_dev_key", None) != key:
+            dev = torch.device("cuda", self.engine.device)
+            c, ns = key[2], key[1]
+            f64, i32 = torch.float64, torch.int32
+            self._dev = dict(ego=torch.empty((b, 6), dtype=f64, device=dev), cost=torch.empty(max(b * c, 1), dtype=f64, device=dev),
+                             flags=torch.empty(max(b * c, 1), dtype=i32, device=dev), idx=torch.empty(b, dtype=i32, device=dev),
+                             best=torch.empty(b, dtype=f64, device=dev), meta=torch.empty((b, 2), dtype=i32, device=dev),
+                             rec=torch.empty((b, _shim.REC_ROWS, ns), dtype=f64, device=dev),
+                             ego_pin=torch.empty((b, 6), dtype=f64).pin_memory())
+            self._dev_key = key
+        return self._dev
+
+    def plan_step_dev(self, stream=None):
+        """One cycle on the device buffers (``self._dev['ego']`` already holds the ego states): the slab's lattice kernel
+        + pick / records, then the cross-GPU pick.  Asynchronous; the results are in ``self._dev`` (idx / best / meta /
+        rec) on every rank."""
+        d, ns = self._dev, self.grid.n_stride
+        if self.local_grid is not None:
+            self.engine.plan_grid_dev(d["ego"], self.local_grid, self.params, d["cost"], d["flags"], None, d["idx"], d["best"],
+                                      d["meta"], d["rec"], ns, stream=stream)
+        else:   # more ranks than lateral rows: this rank has no candidates
+            d["idx"].fill_(-1)
+            d["best"].fill_(float("inf"))
+        if self.world > 1:
+            inner, outer, offset = self.id_map
+            self.engine.allreduce_pick_dev(d["idx"], d["best"], d["meta"], d["rec"], ns, offset, id_inner=inner, id_outer=outer,
+                                           stream=stream)
+
+    def _use_device_path(self) -> bool:
+        return (self.world > 1 and dist.get_backend(self.group) == "nccl" and torch.cuda.is_available()
+                and getattr(self.engine, "comm_world", 1) == self.world)
 
     def plan(self, ego: np.ndarray, device=None) -> dict:
         """``ego [B, 6]`` (same on every rank) -> global winners on every rank."""
         ego = np.ascontiguousarray(np.atleast_2d(ego), dtype=np.float64)
         b = ego.shape[0]
+        if self.world > 1 and dist.get_backend(self.group) == "nccl" and getattr(self.engine, "comm_world", 1) != self.world:
+            self.engine.comm_init(self.group)
+        if self._use_device_path():
+            d = self._device_buffers(b)
+            with torch.cuda.device(self.engine.device):
+                stream = torch.cuda.current_stream()
+                d["ego_pin"].copy_(torch.from_numpy(ego))
+                d["ego"].copy_(d["ego_pin"], non_blocking=True)
+                self.plan_step_dev(stream=stream.cuda_stream)
+                idx, cost = d["idx"].cpu().numpy().astype(np.int64), d["best"].cpu().numpy()   # syncs the stream
+                return dict(best_idx=idx, best_cost=cost, records=d["rec"].cpu().numpy(), meta=d["meta"].cpu().numpy())
         if self.local_grid is not None:
             out = self.engine.plan_grid(ego, self.local_grid, self.params, want_records=True, want_volume=False)
-            idx = np.where(out["best_idx"] >= 0, out["best_idx"].astype(np.int64) + self.id_offset, -1)
+            idx = self.to_global(out["best_idx"])
             cost = np.where(out["best_idx"] >= 0, out["best_cost"], np.inf)
             rec, meta = out["records"], out["meta"]
+            if rec.shape[2] < self.grid.n_stride:       # a slab of short horizons: pad the rows to the full lattice's pitch
+                pad = np.full((b, _shim.REC_ROWS, self.grid.n_stride), np.nan)
+                pad[:, :, :rec.shape[2]] = rec
+                rec = pad
         else:
             idx, cost = np.full(b, -1, np.int64), np.full(b, np.inf)
             rec = np.full((b, _shim.REC_ROWS, self.grid.n_stride), np.nan)

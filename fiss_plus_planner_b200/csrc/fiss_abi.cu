@@ -4,6 +4,8 @@
 // staging and device scratch for the *_host entry points; the *_dev entry points only launch on
 // caller-owned buffers.  Every launch is a persistent grid sized from the SM count and the
 // kernel's occupancy for the shared-memory footprint of the current scene.
+#include <dlfcn.h>
+
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
@@ -12,7 +14,10 @@
 #include <string>
 #include <vector>
 
+#include <nccl.h>  // types and prototypes only: libnccl is resolved at run time (dlopen), never linked
+
 #include "fiss_grid_kernel.cuh"
+#include "fiss_pick_exchange.cuh"
 #include "fiss_spline_kernels.cuh"
 
 namespace {
@@ -184,7 +189,6 @@ struct fiss_handle {
   StepGraph graph_dev, graph_host;  // fiss_plan_grid_dev / the small-batch path of the *_host plan calls
   Lane lanes[kLanes];               // fiss_plan_grid_submit / fiss_plan_grid_wait
   DevBuf d_pick;                    // fiss_allreduce_pick: slot table + record exchange buffer
-  void* nccl_lib = nullptr;         // dlopen handle of libnccl
   void* comm = nullptr;             // ncclComm_t created by fiss_comm_init
   int comm_rank = 0, comm_size = 1;
   size_t smem_attr[8] = {0, 0, 0, 0, 0, 0, 0, 0};
@@ -256,6 +260,52 @@ bool host_is_pinned(const void* p) {
   }
   return at.type == cudaMemoryTypeHost;
 }
+
+// ---- NCCL, resolved at run time ----------------------------------------------------------------
+// libfissgpu.so does not link libnccl: a single-GPU user needs none, and a torch process must end up with ONE copy of
+// the library -- the one torch already loaded -- which dlopen by soname gives.
+struct NcclApi {
+  void* lib = nullptr;
+  ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
+  ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+  ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+  ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+  const char* (*GetErrorString)(ncclResult_t) = nullptr;
+  std::string err;
+} g_nccl;
+
+bool nccl_load(const char* path) {
+  if (g_nccl.AllReduce) return true;
+  void* lib = nullptr;
+  if (path && *path) lib = dlopen(path, RTLD_NOW | RTLD_GLOBAL);
+  if (!lib) lib = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL | RTLD_NOLOAD);  // the copy already in the process
+  if (!lib) lib = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+  if (!lib) lib = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+  if (!lib) {
+    const char* e = dlerror();
+    g_nccl.err = std::string("cannot load libnccl: ") + (e ? e : "unknown error");
+    return false;
+  }
+  g_nccl.lib = lib;
+  g_nccl.GetUniqueId = reinterpret_cast<decltype(g_nccl.GetUniqueId)>(dlsym(lib, "ncclGetUniqueId"));
+  g_nccl.CommInitRank = reinterpret_cast<decltype(g_nccl.CommInitRank)>(dlsym(lib, "ncclCommInitRank"));
+  g_nccl.CommDestroy = reinterpret_cast<decltype(g_nccl.CommDestroy)>(dlsym(lib, "ncclCommDestroy"));
+  g_nccl.AllReduce = reinterpret_cast<decltype(g_nccl.AllReduce)>(dlsym(lib, "ncclAllReduce"));
+  g_nccl.GetErrorString = reinterpret_cast<decltype(g_nccl.GetErrorString)>(dlsym(lib, "ncclGetErrorString"));
+  if (!g_nccl.GetUniqueId || !g_nccl.CommInitRank || !g_nccl.CommDestroy || !g_nccl.AllReduce || !g_nccl.GetErrorString) {
+    g_nccl.err = "libnccl lacks an expected symbol";
+    g_nccl.AllReduce = nullptr;
+    return false;
+  }
+  return true;
+}
+
+#define FISS_NCCL(h, expr)                                                                          \
+  do {                                                                                              \
+    ncclResult_t r_ = (expr);                                                                       \
+    if (r_ != ncclSuccess)                                                                          \
+      return fail(h, FISS_ERR_NCCL, std::string(#expr) + ": " + g_nccl.GetErrorString(r_));         \
+  } while (0)
 
 int32_t check_params(fiss_handle* h, const fiss_params* p) {
   if (!p) return fail(h, FISS_ERR_INVALID, "params is NULL");
@@ -724,6 +774,7 @@ int32_t fiss_destroy(fiss_handle* h) {
   h->graph_host.release();
   h->d_pick.release();
   for (auto& ln : h->lanes) ln.release();
+  if (h->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(static_cast<ncclComm_t>(h->comm));
   if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
   if (h->capture_stream) cudaStreamDestroy(h->capture_stream);
   for (auto& ev : h->part_done)
@@ -1408,6 +1459,91 @@ int32_t fiss_plan_grid_wait(fiss_handle* h, int32_t lane) {
   if (ln.best_meta) std::memcpy(ln.best_meta, ho + w_meta, B * 8);
   if (ln.records && !ln.rec_pinned)
     std::memcpy(ln.records, ho + ((w_bytes + 15) & ~(size_t)15), B * FISS_REC_ROWS * ln.n_stride * 8);
+  return FISS_OK;
+}
+
+// ---- cross-GPU pick ------------------------------------------------------------------------------
+int32_t fiss_comm_unique_id(void* out128, const char* nccl_path) {
+  if (!out128) return fail(nullptr, FISS_ERR_INVALID, "comm_unique_id: out is NULL");
+  if (!nccl_load(nccl_path)) return fail(nullptr, FISS_ERR_NCCL, g_nccl.err);
+  static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId is 128 bytes");
+  ncclUniqueId id;
+  FISS_NCCL(nullptr, g_nccl.GetUniqueId(&id));
+  std::memcpy(out128, &id, sizeof(id));
+  return FISS_OK;
+}
+
+int32_t fiss_comm_init(fiss_handle* h, const void* id128, int32_t nranks, int32_t rank, const char* nccl_path) {
+  if (!h) return FISS_ERR_INVALID;
+  if (!id128 || nranks < 1 || rank < 0 || rank >= nranks) return fail(h, FISS_ERR_INVALID, "comm_init: bad arguments");
+  if (h->comm) return fail(h, FISS_ERR_STATE, "comm_init: the handle already owns a communicator");
+  if (!nccl_load(nccl_path)) return fail(h, FISS_ERR_NCCL, g_nccl.err);
+  FISS_ON_DEVICE(h);
+  ncclUniqueId id;
+  std::memcpy(&id, id128, sizeof(id));
+  ncclComm_t comm = nullptr;
+  FISS_NCCL(h, g_nccl.CommInitRank(&comm, nranks, id, rank));
+  h->comm = comm;
+  h->comm_rank = rank;
+  h->comm_size = nranks;
+  return FISS_OK;
+}
+
+int32_t fiss_comm_destroy(fiss_handle* h) {
+  if (!h) return FISS_ERR_INVALID;
+  if (h->comm) {
+    FISS_ON_DEVICE(h);
+    ncclComm_t comm = static_cast<ncclComm_t>(h->comm);
+    h->comm = nullptr;
+    FISS_NCCL(h, g_nccl.CommDestroy(comm));
+  }
+  h->comm_size = 1;
+  h->comm_rank = 0;
+  return FISS_OK;
+}
+
+int32_t fiss_allreduce_pick(fiss_handle* h, void* comm, int32_t nranks, int32_t rank, void* stream, int32_t B,
+                            int64_t id_inner, int64_t id_outer, int64_t id_offset, int32_t* d_best_idx, double* d_best_cost, int32_t* d_best_meta,
+                            double* d_records, int32_t n_stride) {
+  if (!h) return FISS_ERR_INVALID;
+  if (!d_best_idx || !d_best_cost || B < 1 || (d_records && n_stride < 1))
+    return fail(h, FISS_ERR_INVALID, "allreduce_pick: bad arguments");
+  if (!comm) {  // the handle's own communicator (fiss_comm_init)
+    comm = h->comm;
+    nranks = h->comm_size;
+    rank = h->comm_rank;
+  }
+  if (nranks < 1 || rank < 0 || rank >= nranks) return fail(h, FISS_ERR_INVALID, "allreduce_pick: bad rank / size");
+  if (id_inner < 1 || id_outer < 0 || id_offset < 0) return fail(h, FISS_ERR_INVALID, "allreduce_pick: bad id map");
+  if (nranks > 1 && !comm) return fail(h, FISS_ERR_STATE, "allreduce_pick: no communicator (fiss_comm_init, or pass one)");
+  if (nranks > 1 && !nccl_load(nullptr)) return fail(h, FISS_ERR_NCCL, g_nccl.err);
+  FISS_ON_DEVICE(h);
+  cudaStream_t st = (cudaStream_t)stream;
+  // [slot table B x nranks x 2 | exchange block B x (16 n_stride + 1)] of 64-bit words
+  const size_t table_words = (size_t)B * nranks * 2;
+  const size_t rec_words = d_records ? (size_t)FISS_REC_ROWS * n_stride : 0, xch_words = (size_t)B * (rec_words + 1);
+  FISS_CUDA(h, h->d_pick.ensure((table_words + xch_words) * 8));
+  unsigned long long* table = h->d_pick.as<unsigned long long>();
+  unsigned long long* xch = table + table_words;
+  const int threads = 128;
+  fiss::fiss_pick_pack_kernel<<<(unsigned)((B * nranks + threads - 1) / threads), threads, 0, st>>>(
+      B, nranks, rank, id_inner, id_outer, id_offset, d_best_idx, d_best_cost, table);
+  h->launches++;
+  FISS_CUDA(h, cudaGetLastError());
+  // THE collective of the pick: one all-reduce (MIN over 64-bit keys), 16 B x nranks per problem
+  if (nranks > 1)
+    FISS_NCCL(h, g_nccl.AllReduce(table, table, table_words, ncclUint64, ncclMin, static_cast<ncclComm_t>(comm), st));
+  fiss::fiss_pick_select_kernel<<<(unsigned)B, 256, 0, st>>>(B, nranks, rank, table, d_best_idx, d_best_cost, d_best_meta,
+                                                            d_records, (int)rec_words, xch);
+  h->launches++;
+  FISS_CUDA(h, cudaGetLastError());
+  // the winners' records travel from their owners: every other rank contributes zero words to an integer SUM, which
+  // reproduces the owner's bit patterns exactly (NaN payloads included) -- no root, hence no host round trip
+  if (nranks > 1)
+    FISS_NCCL(h, g_nccl.AllReduce(xch, xch, xch_words, ncclUint64, ncclSum, static_cast<ncclComm_t>(comm), st));
+  fiss::fiss_pick_unpack_kernel<<<(unsigned)B, 256, 0, st>>>(B, xch, d_best_idx, d_best_meta, d_records, (int)rec_words);
+  h->launches++;
+  FISS_CUDA(h, cudaGetLastError());
   return FISS_OK;
 }
 

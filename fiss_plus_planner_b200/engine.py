@@ -142,6 +142,7 @@ class FissEngine:
         # (or a planner and its lazy candidate bundles) sharing one engine can tell that the tables are no longer theirs
         self.spline_token = 0
         self.obstacle_token = 0
+        self.comm_world, self.comm_rank = 1, 0
         self._ego_stage = np.zeros((self._STAGE_ROWS, 6), np.float64)
         self._ego_stage_ptr = _shim.ptr(self._ego_stage)
 
@@ -362,6 +363,37 @@ class FissEngine:
             self._h, self._stream(stream), vp(ego_t), ego_t.shape[0], C.byref(grid.c_struct), C.byref(params), vp(cost_t),
             vp(flags_t), vp(mat_t), vp(best_idx_t), vp(best_cost_t), vp(meta_t), vp(records_t), int(n_stride)),
             "fiss_plan_grid_dev")
+
+    # ------------------------------------------------------------------ multi-GPU pick (NCCL inside the C-ABI)
+    def comm_init(self, group=None, nccl_path: str = None):
+        """Create the handle's own NCCL communicator over the ranks of ``group`` (torch.distributed is only the
+        out-of-band channel for the 128-byte unique id).  ``fiss_allreduce_pick`` then runs on it."""
+        import torch
+        import torch.distributed as dist
+        world, rank = dist.get_world_size(group), dist.get_rank(group)
+        path = nccl_path.encode() if nccl_path else None
+        ident = (C.c_ubyte * 128)()
+        if rank == 0:
+            self._check(self._lib.fiss_comm_unique_id(ident, path), "fiss_comm_unique_id")
+        box = [bytes(ident)]
+        dist.broadcast_object_list(box, src=dist.get_global_rank(group, 0) if group is not None else 0, group=group)
+        ident = (C.c_ubyte * 128).from_buffer_copy(box[0])
+        torch.cuda.synchronize(self.device)
+        self._check(self._lib.fiss_comm_init(self._h, ident, world, rank, path), "fiss_comm_init")
+        self.comm_world, self.comm_rank = world, rank
+
+    def comm_destroy(self):
+        self._check(self._lib.fiss_comm_destroy(self._h), "fiss_comm_destroy")
+        self.comm_world, self.comm_rank = 1, 0
+
+    def allreduce_pick_dev(self, best_idx_t, best_cost_t, meta_t, records_t, n_stride: int, id_offset: int,
+                           id_inner: int = 1 << 40, id_outer: int = 0, stream=None):
+        """In place on device buffers: local slab winners -> the global winners on every rank (``fiss_allreduce_pick``
+        on the handle's communicator): one all-reduce for the pick, one for the winners' records, no host sync."""
+        vp = lambda t: C.c_void_p(t.data_ptr()) if t is not None else None  # noqa: E731
+        self._check(self._lib.fiss_allreduce_pick(self._h, None, 0, 0, self._stream(stream), best_idx_t.shape[0],
+                                                  int(id_inner), int(id_outer), int(id_offset), vp(best_idx_t), vp(best_cost_t), vp(meta_t), vp(records_t),
+                                                  int(n_stride)), "fiss_allreduce_pick")
 
     def pick_winners_dev(self, ego_t, end_t, params: FissParams, cost_t, flags_t, best_idx_t, best_cost_t,
                          records_t, meta_t, n_stride: int, stream=None):

@@ -30,7 +30,8 @@ enum {
   FISS_ERR_INVALID = -1,  /* bad argument */
   FISS_ERR_CUDA = -2,     /* a CUDA runtime call failed; see fiss_last_error */
   FISS_ERR_CAPACITY = -3, /* request exceeds what one launch supports */
-  FISS_ERR_STATE = -4     /* spline not set, ... */
+  FISS_ERR_STATE = -4,    /* spline not set, lane busy, no communicator, ... */
+  FISS_ERR_NCCL = -5      /* libnccl could not be loaded or an NCCL call failed; see fiss_last_error */
 };
 
 /* per-candidate flags word written by the device */
@@ -221,6 +222,31 @@ int32_t fiss_plan_grid_wait(fiss_handle* h, int32_t lane);
 int32_t fiss_eval_end_states_host(fiss_handle* h, void* stream, const double* ego6, const double* end,
                                   int32_t N, const fiss_params* p, double* cost, uint32_t* flags,
                                   double* records, int32_t n_stride);
+
+/* ---- multi-GPU: the cross-GPU best-cost pick (BASELINE config 5 with few problems) ------------------ */
+/* One lattice can be split across the GPUs of a box: rank r evaluates a slab of it -- some lateral rows, or some
+ * horizons -- and picks the slab's winner (fiss_plan_grid_dev on the slab's own fiss_grid).  Local candidate id c maps
+ * to the id of FrenetOptimalPlanner's full numbering as (c / id_inner) * id_outer + c % id_inner + id_offset: a slab of
+ * lateral rows [i_lo, i_hi) is a contiguous range (id_inner >= C_local, id_offset = i_lo * stride_d); a slab of
+ * horizons [k_lo, k_hi) is (k_hi - k_lo) * nv consecutive ids out of every nt * nv (id_inner = (k_hi - k_lo) * nv,
+ * id_outer = nt * nv, id_offset = k_lo * nv).  Either way the local order is the global order restricted.  fiss_allreduce_pick then makes every rank hold the GLOBAL winner under the reference's rule --
+ * minimum cost, the LAST minimum in enumeration order on exact ties (frenet_optimal_planner.py:263-268) -- with
+ *   * ONE ncclAllReduce(MIN, uint64) for the pick: a [B][nranks][2] slot table of (order-preserving cost key, global id),
+ *     each rank filling its own slot (a float64 cost and an id do not fit one 64-bit key without dropping cost bits);
+ *   * one ncclAllReduce(SUM, uint64) that moves the winners' records (+ (n, n')) from their owners -- the other ranks
+ *     add zero words, so the bit patterns arrive exact; no root rank, hence no host round trip.
+ * Everything is enqueued on `stream`; nothing synchronises.  In place: d_best_idx [B] local ids (-1 = none) -> global
+ * ids, d_best_cost [B] -> the global minima (+inf = none), d_best_meta [B][2] and d_records [B][FISS_REC_ROWS][n_stride]
+ * (either may be NULL) -> the global winner's (all-NaN record where nothing is feasible).
+ * `comm` is an ncclComm_t of the caller (with its nranks / rank), or NULL for the communicator the handle owns
+ * (fiss_comm_init).  libnccl is resolved at run time (the copy already in the process, e.g. torch's, else libnccl.so.2;
+ * nccl_path may name one explicitly or be NULL); a single-GPU user never loads it. */
+int32_t fiss_comm_unique_id(void* out128, const char* nccl_path);                       /* ncclGetUniqueId: 128 bytes */
+int32_t fiss_comm_init(fiss_handle* h, const void* id128, int32_t nranks, int32_t rank, const char* nccl_path);
+int32_t fiss_comm_destroy(fiss_handle* h);
+int32_t fiss_allreduce_pick(fiss_handle* h, void* comm, int32_t nranks, int32_t rank, void* stream, int32_t B,
+                            int64_t id_inner, int64_t id_outer, int64_t id_offset, int32_t* d_best_idx, double* d_best_cost, int32_t* d_best_meta,
+                            double* d_records, int32_t n_stride);
 
 /* number of kernel launches issued through this handle so far (bench.py's gpu_launches) */
 int64_t fiss_launch_count(const fiss_handle* h);

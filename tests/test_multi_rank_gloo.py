@@ -69,14 +69,16 @@ def _worker(rank, world, port, q):
         pick = (cost.tolist(), idx.tolist())
         # --- split lattice
         grid, ego = _grid(), _ego()
-        sp = SplitLatticePlanner(FakeEngine(), grid, None)
+        sp = SplitLatticePlanner(FakeEngine(), grid, None, axis="d")
         out = sp.plan(ego)
+        sp_t = SplitLatticePlanner(FakeEngine(), grid, None, axis="t")            # slabs of horizons: strided global ids
+        out_t = sp_t.plan(ego)
         # --- sharded batch + gather
         sb = ShardedBatchPlanner(FakeEngine(), grid, None)
         loc = sb.plan_local(ego)
         gi, gc = sb.gather_winners(loc, len(ego))
-        q.put((rank, pick, {k: np.asarray(v) for k, v in out.items()}, (sp.i_lo, sp.i_hi), loc["problems"], gi, gc,
-               shard_range(10, world, rank)))
+        q.put((rank, pick, {k: np.asarray(v) for k, v in out.items()}, (sp.lo, sp.hi), loc["problems"], gi, gc,
+               shard_range(10, world, rank), {k: np.asarray(v) for k, v in out_t.items()}, (sp_t.lo, sp_t.hi)))
     finally:
         dist.destroy_process_group()
 
@@ -96,7 +98,9 @@ def test_world2_gloo_pick_split_and_shard():
         assert p.exitcode == 0
 
     ref = SplitLatticePlanner(FakeEngine(), _grid(), None).plan(_ego())            # single rank, whole lattice
-    for rank, pick, out, rows, problems, gi, gc, sr in res:
+    for rank, pick, out, rows, problems, gi, gc, sr, out_t, horizons in res:
+        for k in ("best_idx", "best_cost", "meta", "records"):
+            np.testing.assert_array_equal(out_t[k], ref[k], err_msg="horizon split: " + k)
         # min cost; among equal minima the LARGEST index (frenet_optimal_planner.py:263-268); -1 when nobody has one
         assert pick == ([1.0, 1.5, float("inf"), 5.0, 3.0], [10, 9, -1, 2, 40])
         np.testing.assert_array_equal(out["best_idx"], ref["best_idx"])
@@ -109,8 +113,38 @@ def test_world2_gloo_pick_split_and_shard():
     # problem 0 ties the d = -0.4 and d = +0.4 rows (different ranks): the larger id, i.e. the +0.4 row, wins
     assert _grid().table()[ref["best_idx"][0], 0] == pytest.approx(0.4)
     assert [r[3] for r in res] == [(0, 5), (5, 9)]                                  # lateral rows per rank
+    assert [r[9] for r in res] == [(0, 3), (3, 5)]                                  # horizons per rank
     assert [r[4] for r in res] == [(0, 2), (2, 4)]                                  # problems per rank
     assert [r[7] for r in res] == [(0, 5), (5, 10)]
+
+
+def test_split_id_maps_are_order_preserving_bijections():
+    """Local candidate ids of every slab map onto the full lattice's ids: together a partition, each map monotone (so
+    the slab's "last minimum" is the global numbering's)."""
+    from fiss_plus_planner_b200.batch import SplitLatticePlanner
+    from fiss_plus_planner_b200.engine import LatticeGrid
+    grid = LatticeGrid(np.linspace(-1, 1, 33), np.linspace(0, 13, 17), np.linspace(8, 10, 9), 0.1, "dtv")
+    full = grid.table()
+    for axis in ("t", "d"):
+        for world in (1, 2, 3, 4, 8, 12):
+            seen = []
+            for rank in range(world):
+                sp = SplitLatticePlanner.__new__(SplitLatticePlanner)
+                sp.world, sp.rank = world, rank
+                import fiss_plus_planner_b200.batch as batch
+                orig = batch._world
+                batch._world = lambda group=None, w=world, r=rank: (w, r)
+                try:
+                    sp.__init__(FakeEngine(), grid, None, axis=axis)
+                finally:
+                    batch._world = orig
+                if sp.local_grid is None:
+                    continue
+                g = sp.to_global(np.arange(sp.local_grid.num_candidates))
+                assert (np.diff(g) > 0).all()
+                np.testing.assert_array_equal(sp.local_grid.table(), full[g])      # the same end states, the same order
+                seen.append(g)
+            np.testing.assert_array_equal(np.sort(np.concatenate(seen)), np.arange(grid.num_candidates))
 
 
 def test_shard_range_is_a_partition():
