@@ -681,7 +681,7 @@ int32_t eval_grid(fiss_handle* h, cudaStream_t st, const double* d_ego, int B, c
                        n_blocks * n_groups * n_groups < (1 << 20) && (int64_t)a.slots * a.C * n_stride < ((int64_t)1 << 31) &&
                        base_items * g->nt < ((int64_t)1 << 32);
     a.E_stage = E_max;
-    L = fiss::grid_layout(a.Kp, a.Mp, a.E_stage, a.nv, a.d_chunk, a.n_pad, a.e_pad, a.words, a.slots, a.lut_bytes);
+    L = fiss::grid_layout(a.Kp, a.Mp, a.E_stage, a.nv, a.d_chunk, a.n_pad, a.e_pad, a.words, a.slots, a.lut_bytes, yaw);
     // ... and the items must deal evenly over the resident CTAs: the launch lasts ceil(items / CTAs) item times
     // (640 four-slot items on 296 CTAs: 3 rounds, 72 % busy; 854 three-slot items: 3 rounds, 96 %)
     const int64_t items_s = (base_items + a.slots - 1) / a.slots, ctas = (int64_t)min_ctas * h->sm_count;
@@ -694,7 +694,7 @@ int32_t eval_grid(fiss_handle* h, cudaStream_t st, const double* d_ego, int B, c
     if (!exact) return fail(h, FISS_ERR_CAPACITY, "lattice or batch too large for the kernel's index arithmetic (nv * n_stride^2 < 2^20, B * nt^2 < 2^32)");
     if (L.bytes > kSmemCtaBudget) {
       a.E_stage = 0;
-      L = fiss::grid_layout(a.Kp, a.Mp, a.E_stage, a.nv, a.d_chunk, a.n_pad, a.e_pad, a.words, a.slots, a.lut_bytes);
+      L = fiss::grid_layout(a.Kp, a.Mp, a.E_stage, a.nv, a.d_chunk, a.n_pad, a.e_pad, a.words, a.slots, a.lut_bytes, yaw);
     }
     break;
   }

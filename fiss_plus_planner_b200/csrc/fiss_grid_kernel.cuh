@@ -95,7 +95,7 @@ constexpr int kMatRows = FISS_MAT_GROUP;  // lateral rows one materialisation ta
 
 // Shared-memory carve-up (byte offsets, 16-byte aligned), used by the host for the launch size too.
 struct GridLayout {
-  uint32_t spline, oc, obs, bbox, bbox_key, axes, slot_d, slot_base, slot_off, lon, lat, lon_cost, lat_cost, dmax, lon_viol,
+  uint32_t spline, oc, obs, bbox, bbox_key, axes, slot_d, slot_base, slot_off, lon, th, lat, lon_cost, lat_cost, dmax, lon_viol,
       lon_ncart, lon_E, counters, pairs, cflags, masks, listed, near_list, bytes;
 };
 
@@ -140,7 +140,7 @@ struct GridArgs {
 __host__ __device__ inline uint32_t grid_align16(uint32_t v) { return (v + 15u) & ~15u; }
 
 __host__ __device__ inline GridLayout grid_layout(int Kp, int Mp, int E_stage, int nv, int d_chunk, int n_pad, int e_pad,
-                                                  int words, int slots, int lut_bytes) {
+                                                  int words, int slots, int lut_bytes, bool yaw = false) {
   GridLayout L;
   const uint32_t lon_rows = (uint32_t)slots * nv, lat_rows = (uint32_t)slots * d_chunk;
   uint32_t o = 16;  // two mbarriers
@@ -154,6 +154,7 @@ __host__ __device__ inline GridLayout grid_layout(int Kp, int Mp, int E_stage, i
   L.slot_base = o;  o += 2u * kMaxSlots * 8u;        // [2][kMaxSlots] id of the slot's candidate (i0, 0, k)
   L.slot_off = o;   o += 2u * kMaxSlots * 4u;        // [2][kMaxSlots] the same relative to slot 0, in output elements
   L.lon = o;        o += grid_align16(5u * lon_rows * n_pad * 8u);
+  L.th = o;         o += yaw ? grid_align16(lon_rows * n_pad * 8u) : 0u;  // reference-line heading per (row, step): materialising kernel only
   L.lat = o;        o += grid_align16(lat_rows * n_pad * 8u);
   L.lon_cost = o;   o += grid_align16(lon_rows * 8u);
   L.lat_cost = o;   o += grid_align16(lat_rows * 8u);
@@ -209,8 +210,8 @@ struct MatOut {
 
 template <int R>
 __device__ __forceinline__ void mat_rows(const GridArgs& a, const MatOut& mo, const double2 Pa, const double2 Ua, const double2 Pb,
-                                         const double2 Ub, double sd_v, const double* __restrict__ Dr, int n_pad, int off,
-                                         int lat_pitch, uint32_t* cf, int nv) {
+                                         const double2 Ub, double th, double sd_v, const double* __restrict__ Dr, int n_pad,
+                                         int off, int lat_pitch, uint32_t* cf, int nv) {
   double dx[R], dy[R], yaw[R], inv_ds[R], kap[R];
   bool ok[R];
 #pragma unroll
@@ -230,8 +231,14 @@ __device__ __forceinline__ void mat_rows(const GridArgs& a, const MatOut& mo, co
 #ifdef FISS_EXP_NOMATH
 #pragma unroll
   for (int r = 0; r < R; ++r) { yaw[r] = dx[r]; inv_ds[r] = dy[r]; ok[r] = true; }
-#else
+#elif defined(FISS_NO_FRAME_HEADING)
   segment_fast_n<R>(dx, dy, yaw, inv_ds, ok);
+#else
+  // heading relative to the reference line's tangent: the short polynomial when every segment of the task stays within
+  // atan(0.3) of it (lanes without a segment -- NaN frame points -- do not vote); else the full-octant path
+  bool narrow;
+  segment_frame_n<R>(dx, dy, Ua.x, Ua.y, th, yaw, inv_ds, ok, narrow);
+  if (__any_sync(kFull, mo.has_seg && !narrow)) segment_fast_n<R>(dx, dy, yaw, inv_ds, ok);
 #endif
   // a zero-length / non-finite segment takes the library (its special cases are the reference's)
   bool any_odd = false;
@@ -323,6 +330,7 @@ __global__ void __launch_bounds__(grid_warps(kYaw) * 32, grid_min_ctas(kYaw)) fi
   double2* P2 = reinterpret_cast<double2*>(lon);                // [slots * nv][n_pad] frame point (px, py)
   double2* U2 = reinterpret_cast<double2*>(lon + 2 * row_len);  // [slots * nv][n_pad] unit tangent (ux, uy)
   double* SD = lon + 4 * row_len;                               // [slots * nv][n_pad] longitudinal speed
+  double* TH = reinterpret_cast<double*>(smem_raw + L.th);      // [slots * nv][n_pad] heading of the reference line (kYaw)
 
   // ---- stage 0: tables.  The spline is needed first (stage A); the obstacle rows only in stage A'.
   if (threadIdx.x == 0) {
@@ -435,7 +443,7 @@ __global__ void __launch_bounds__(grid_warps(kYaw) * 32, grid_min_ctas(kYaw)) fi
     __syncthreads();
     // last item of this CTA: a dependent launch (the record kernel, fiss_pick_winners_dev) may start staging its tables
     if (item + gridDim.x >= n_items) pdl_launch_dependents();
-#ifdef FISS_EARLY_SLOTS
+#ifndef FISS_LATE_SLOTS
     // the next item's slots: the other buffer is free from here on, and the global loads complete under stage A (issued
     // at the end of stage C, their latency was exposed at this barrier)
     load_slots(item + gridDim.x, par ^ 1);
@@ -498,6 +506,7 @@ __global__ void __launch_bounds__(grid_warps(kYaw) * 32, grid_min_ctas(kYaw)) fi
           if (okA) {
             P2[base + m0] = make_double2(pxA, pyA);
             U2[base + m0] = make_double2(txA * rA, tyA * rA);
+            if (kYaw) TH[base + m0] = atan2_finite(tyA, txA);
           } else {
             first_bad = min(first_bad, m0);
           }
@@ -506,6 +515,7 @@ __global__ void __launch_bounds__(grid_warps(kYaw) * 32, grid_min_ctas(kYaw)) fi
             if (okB) {
               P2[base + m1] = make_double2(pxB, pyB);
               U2[base + m1] = make_double2(txB * rB, tyB * rB);
+              if (kYaw) TH[base + m1] = atan2_finite(tyB, txB);
             } else {
               first_bad = min(first_bad, m1);
             }
@@ -775,6 +785,7 @@ __global__ void __launch_bounds__(grid_warps(kYaw) * 32, grid_min_ctas(kYaw)) fi
         const double sd_v = m < n ? SD[jj * n_pad + min(m, n_pad - 1)] : CUDART_NAN;
         const double2 Pa = fp[0], Pb = fp[1];
         const double2 Ua = fp[row_len], Ub = fp[row_len + 1];  // U2 = P2 + row_len
+        const double th = TH[jj * n_pad + seg];
         const int i_first = grp * kMatRows;
         const int ll = g * dc + i_first;  // first lateral row of the group in the lane's slot
         const double* Dr = lat + ll * n_pad + seg;
@@ -783,9 +794,9 @@ __global__ void __launch_bounds__(grid_warps(kYaw) * 32, grid_min_ctas(kYaw)) fi
         const int rows_here = min(kMatRows, rows_i - i_first);  // warp-uniform
         int r = 0;
         for (; r + kMatIlp <= rows_here; r += kMatIlp)
-          mat_rows<kMatIlp>(a, mo, Pa, Ua, Pb, Ub, sd_v, Dr + r * n_pad, n_pad, off + r * lat_pitch, lat_pitch, cf + r * nv, nv);
+          mat_rows<kMatIlp>(a, mo, Pa, Ua, Pb, Ub, th, sd_v, Dr + r * n_pad, n_pad, off + r * lat_pitch, lat_pitch, cf + r * nv, nv);
         for (; r < rows_here; ++r)
-          mat_rows<1>(a, mo, Pa, Ua, Pb, Ub, sd_v, Dr + r * n_pad, n_pad, off + r * lat_pitch, lat_pitch, cf + r * nv, nv);
+          mat_rows<1>(a, mo, Pa, Ua, Pb, Ub, th, sd_v, Dr + r * n_pad, n_pad, off + r * lat_pitch, lat_pitch, cf + r * nv, nv);
       }
     }
     __syncthreads();
@@ -815,7 +826,7 @@ __global__ void __launch_bounds__(grid_warps(kYaw) * 32, grid_min_ctas(kYaw)) fi
         a.flags[out_id] = viol | extra | ((uint32_t)n_cart << FISS_FLAG_NCART_SHIFT);
       }
       reset_item_state();
-#ifndef FISS_EARLY_SLOTS
+#ifdef FISS_LATE_SLOTS
       load_slots(item + gridDim.x, par ^ 1);
 #endif
     }
