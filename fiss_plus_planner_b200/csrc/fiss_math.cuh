@@ -218,11 +218,20 @@ __device__ __forceinline__ void segment_frame_n(const double (&dx)[R], const dou
   for (int i = 0; i < R; ++i) pe[i] = fma(u[i], po[i], pe[i]);
 #pragma unroll
   for (int i = 0; i < R; ++i) po[i] = q[i] * u[i];
+  bool outside = false;
 #pragma unroll
   for (int i = 0; i < R; ++i) {
-    const double y0 = th + fma(po[i], pe[i], q[i]);
-    const double y1 = y0 > 3.141592653589793 ? y0 - 6.283185307179586 : y0;
-    yaw[i] = y1 <= -3.141592653589793 ? y1 + 6.283185307179586 : y1;
+    yaw[i] = th + fma(po[i], pe[i], q[i]);
+    outside = outside || fabs(yaw[i]) > 3.141592653589793;  // (false for the NaN of a lane without a segment)
+  }
+  // th is in (-pi, pi] and |atan(q)| < 0.3: the sum leaves that range only where the road itself points (almost) along
+  // -x -- one warp-uniform vote keeps the two selects per segment off the common path
+  if (__any_sync(0xffffffffu, outside)) {
+#pragma unroll
+    for (int i = 0; i < R; ++i) {
+      const double y1 = yaw[i] > 3.141592653589793 ? yaw[i] - 6.283185307179586 : yaw[i];
+      yaw[i] = y1 <= -3.141592653589793 ? y1 + 6.283185307179586 : y1;
+    }
   }
   // rsqrt_normal
   double y[R];

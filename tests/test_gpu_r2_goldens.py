@@ -114,3 +114,54 @@ def test_trajectories_vs_reference(path):
             np.testing.assert_allclose(rec[row, r_row, :len(want)], want, err_msg=f"record {f} cand {c}", **tol)
             np.testing.assert_allclose(mat[m_row, c, :len(want)], want, err_msg=f"materialised {f} cand {c}", **tol)
             assert np.isnan(mat[m_row, c, len(want):]).all()
+
+
+def test_heading_wraps_like_arctan2_on_a_westbound_road():
+    """The lattice kernel forms a candidate's heading as (reference-line heading) + atan(lateral / longitudinal progress)
+    and wraps the sum into (-pi, pi].  On a road that runs along -x the headings straddle +-pi: yaw must jump exactly where
+    numpy's arctan2 does, and kappa -- differenced WITHOUT unwrapping by the reference (frenet_optimal_planner.py:132) --
+    must show the same 2 pi / ds spikes.  Oracle comparison on every candidate of a 5x4x3 lattice, both kernels."""
+    import torch
+    from fiss_plus_planner_b200 import synthetic as syn
+    from fiss_plus_planner_b200.engine import FissEngine, fop_grid, make_params
+    from fiss_plus_planner_b200.planners.common.cost.cost_function import CostFunction
+    from fiss_plus_planner_b200.planners.common.geometry.cubic_spline import CubicSpline2D
+    from fiss_plus_planner_b200.planners.common.vehicle.vehicle import Vehicle
+    from fiss_plus_planner_b200.planners.frenet_optimal_planner import FrenetOptimalPlannerSettings
+    from oracle import fop_oracle as fo
+    k = np.arange(61)
+    line = np.column_stack((-5.0 * k + 465.7, 3.0 * np.sin(5.0 * k / 30.0) - 304.8))      # heading ~ pi, wiggling across it
+    veh = Vehicle(syn.vehicle_params())
+    st = FrenetOptimalPlannerSettings(5, 4, 3)
+    st.min_t, st.max_t, st.highest_speed = 4.0, 5.0, 13.4112
+    eng = FissEngine(0)
+    eng.set_spline(CubicSpline2D(line[:, 0], line[:, 1]).device_table())
+    eng.set_obstacles(None, np.zeros((0, 2)), None, 0)
+    grid = fop_grid(st, veh.w)
+    prm = make_params(st, veh, CostFunction("WX1").as_device_weights())
+    egos = np.array([[20.0, 9.0, 0.2, 0.3, -0.2, 0.1], [95.0, 4.0, -0.3, -0.5, 0.25, 0.0], [150.0, 12.0, 0.0, 0.0, 0.0, 0.0]])
+    dev = torch.device("cuda", 0)
+    b, c, ns = len(egos), grid.num_candidates, grid.n_stride
+    ego_t = torch.tensor(egos, dtype=torch.float64, device=dev)
+    cost_t = torch.empty(b * c, dtype=torch.float64, device=dev)
+    flags_t = torch.empty(b * c, dtype=torch.int32, device=dev)
+    mat_t = torch.empty((5, b * c, ns), dtype=torch.float64, device=dev)
+    eng.eval_grid_dev(ego_t, grid, prm, cost_t, flags_t, mat_t, ns, stream=torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    mat = mat_t.cpu().numpy().reshape(5, b, c, ns)
+    ost = fo.Settings(5, 4, 3)
+    ost.min_t, ost.max_t, ost.highest_speed = 4.0, 5.0, 13.4112
+    opl = fo.FopOracle(ost, veh.l, veh.w, veh.max_speed, veh.max_accel)
+    sp = opl.generate_frenet_frame(line)
+    wraps = 0
+    for bi, ego in enumerate(egos):
+        rec = eng.eval_end_states(ego, grid.table(), prm, want_records=True)["records"]          # list kernel
+        for ci, (d, v, T) in enumerate(opl.lattice()):
+            tr = fo.to_global(fo.generate(fo.Traj(), tuple(ego), d, v, T, 0.1, 13.4112), sp, 0.1)
+            n1 = len(tr.x)
+            assert n1 >= 2
+            for got_yaw, got_c in ((mat[2, bi, ci], mat[4, bi, ci]), (rec[ci, 11], rec[ci, 13])):
+                np.testing.assert_allclose(got_yaw[:n1], tr.yaw, rtol=0, atol=ATOL_YAW)
+                np.testing.assert_allclose(got_c[:n1 - 1], tr.c, rtol=1e-4, atol=ATOL_KAPPA)
+            wraps += int(np.count_nonzero(np.abs(np.diff(tr.yaw)) > 6.0))
+    assert wraps > 20, "the scene must actually cross +-pi"
