@@ -85,3 +85,20 @@ def test_stats_and_trajectory_helpers():
     assert (st.x, st.v) == (1.0, rec[2, 1])
     short = FrenetTrajectory().fill_from_device_record(rec, 5, 1, 0.0)
     assert len(short.x) == 1 and len(short.yaw) == 0
+
+
+def test_shapes_that_are_not_origin_rectangles_are_refused():
+    import types
+    import pytest
+    from fiss_plus_planner_b200.planners.frenet_optimal_planner import marshal_obstacles
+    pred = types.SimpleNamespace(final_time_step=3)
+    st = types.SimpleNamespace(position=np.zeros(2), orientation=0.0)
+    mk = lambda shape: [types.SimpleNamespace(prediction=pred, obstacle_shape=shape, state_at_time=lambda t: st)]  # noqa: E731
+    ok = marshal_obstacles(mk(types.SimpleNamespace(length=4.0, width=2.0)))
+    assert ok.lw.tolist() == [[4.0, 2.0]]
+    with pytest.raises(NotImplementedError):
+        marshal_obstacles(mk(types.SimpleNamespace(radius=1.0)))                                    # a circle
+    with pytest.raises(NotImplementedError):
+        marshal_obstacles(mk(types.SimpleNamespace(length=4.0, width=2.0, center=np.array([1.0, 0.0]))))
+    with pytest.raises(NotImplementedError):
+        marshal_obstacles(mk(types.SimpleNamespace(length=4.0, width=2.0, orientation=0.3)))
