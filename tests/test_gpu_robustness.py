@@ -116,3 +116,49 @@ def test_no_obstacles_and_many_obstacles():
     torch.cuda.synchronize()
     np.testing.assert_array_equal(out["flags"].ravel(), flags_t.cpu().numpy().astype(np.uint32))   # lattice == list kernel
     assert ((out["flags"] & _shim.FLAG_COLLISION) != 0).any()
+
+
+def test_round2_entry_points_reject_bad_arguments():
+    """fiss_plan_grid_dev / _submit / _wait, fiss_set_obstacles_waymo, fiss_allreduce_pick: status codes, messages, and a
+    handle that keeps working afterwards."""
+    import ctypes as C
+    import torch
+    from fiss_plus_planner_b200 import _shim
+    from fiss_plus_planner_b200._shim import FissError
+    sc, eng, grid, prm = _setup(batch=3)
+    lib = _shim.load()
+    h, g, pp = eng._h, C.byref(grid.c_struct), C.byref(prm)
+    assert lib.fiss_plan_grid_dev(h, None, None, 3, g, pp, None, None, None, None, None, None, None, grid.n_stride) == -1
+    assert b"plan_grid_dev" in lib.fiss_last_error(h)
+    out = eng.alloc_plan_outputs(3, grid, want_records=True, want_volume=False, pinned=False)
+    with pytest.raises(FissError, match="lane"):
+        eng.plan_grid_submit(7, sc.ego, grid, prm, out)
+    with pytest.raises(FissError, match="nothing in flight"):
+        eng.plan_grid_wait(0)
+    with pytest.raises(FissError, match="n_stride"):
+        short = dict(out)
+        short.pop("_ptrs", None)
+        lib_rc = lib.fiss_plan_grid_submit(h, None, 0, _shim.ptr(sc.ego), 3, g, pp, _shim.ptr(out["best_idx"]),
+                                           _shim.ptr(out["best_cost"]), _shim.ptr(out["meta"]), _shim.ptr(out["records"]), 3)
+        eng._check(lib_rc, "fiss_plan_grid_submit")
+    eng.plan_grid_submit(0, sc.ego, grid, prm, out)         # the failed submit left the lane free
+    eng.plan_grid_wait(0)
+    ref = eng.plan_grid(sc.ego, grid, prm, want_records=True)
+    np.testing.assert_array_equal(out["best_idx"], ref["best_idx"])
+    np.testing.assert_array_equal(out["records"], ref["records"])
+    # Waymo tensors: wrong shapes are refused before anything is uploaded
+    assert lib.fiss_set_obstacles_waymo(h, None, None, None, 4, 10, -1, None) == -1
+    assert lib.fiss_set_obstacles_waymo(h, None, None, None, 0, 0, -1, None) == 0          # N = 0: the table is cleared
+    assert not (eng.plan_grid(sc.ego, grid, prm, want_volume=True)["flags"] & 8).any()    # ... no collisions any more
+    # cross-GPU pick without a communicator: nranks > 1 needs one; a handle without one is a single rank
+    dev = torch.device("cuda", 0)
+    idx = torch.zeros(3, dtype=torch.int32, device=dev)
+    best = torch.zeros(3, dtype=torch.float64, device=dev)
+    vp = lambda t: C.c_void_p(t.data_ptr())  # noqa: E731
+    assert lib.fiss_allreduce_pick(h, C.c_void_p(1), 2, 5, None, 3, 1, 0, 0, vp(idx), vp(best), None, None, 0) == -1   # rank >= size
+    assert lib.fiss_allreduce_pick(h, None, 0, 0, None, 3, 0, 0, 0, vp(idx), vp(best), None, None, 0) == -1            # id map
+    assert b"id map" in lib.fiss_last_error(h)
+    assert lib.fiss_allreduce_pick(h, None, 0, 0, None, 3, 1 << 40, 0, 7, vp(idx), vp(best), None, None, 0) == 0
+    torch.cuda.synchronize()
+    assert idx.cpu().tolist() == [7, 7, 7]
+    assert lib.fiss_comm_destroy(h) == 0                    # nothing to destroy: fine
