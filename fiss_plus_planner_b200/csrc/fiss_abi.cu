@@ -18,6 +18,7 @@
 
 #include "fiss_grid_kernel.cuh"
 #include "fiss_pick_exchange.cuh"
+#include "fiss_record_kernel.cuh"
 #include "fiss_spline_kernels.cuh"
 
 namespace {
@@ -191,10 +192,10 @@ struct fiss_handle {
   DevBuf d_pick;                    // fiss_allreduce_pick: slot table + record exchange buffer
   void* comm = nullptr;             // ncclComm_t created by fiss_comm_init
   int comm_rank = 0, comm_size = 1;
-  size_t smem_attr[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  size_t smem_attr[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
   // resident CTAs per SM of kernel `which` at (threads, smem): asked from the runtime once per distinct launch shape
   // (the query costs microseconds on the latency path of every plan() call)
-  struct OccKey { int threads = -1; size_t smem = 0; int occ = 1; } occ_cache[8];
+  struct OccKey { int threads = -1; size_t smem = 0; int occ = 1; } occ_cache[12];
   template <typename K>
   cudaError_t occupancy(int which, K kern, int threads, size_t smem, int* out) {
     OccKey& c = occ_cache[which];
@@ -366,6 +367,30 @@ int32_t launch_eval(fiss_handle* h, cudaStream_t st, LaunchPlan& lp, int which) 
   kl.smem = lp.smem;
   kl.pdl = lp.a.after_producer != 0;
   kl.push(lp.a);
+  return issue(h, st, kl);
+}
+
+// The winners' records with the pick fused in (fiss_record_kernel.cuh): W warps per problem.
+template <int W>
+int32_t launch_record(fiss_handle* h, cudaStream_t st, const fiss::EvalArgs& a, int which) {
+  auto kern = fiss::fiss_record_kernel<W>;
+  const size_t smem = fiss::record_smem_bytes(a.Kp, a.n_pad, W);
+  if (smem > kSmemLimit) return fail(h, FISS_ERR_CAPACITY, "spline table too large for the record kernel's shared memory");
+  if (smem > 48 * 1024 && smem > h->smem_attr[which]) {
+    FISS_CUDA(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemLimit));
+    h->smem_attr[which] = kSmemLimit;
+  }
+  int occ = 1;
+  FISS_CUDA(h, h->occupancy(which, kern, fiss::kRecWarps * 32, smem, &occ));
+  constexpr int per_cta = fiss::kRecWarps / W;
+  const int64_t need = (a.total + per_cta - 1) / per_cta;
+  KernelLaunch kl;
+  kl.func = (const void*)kern;
+  kl.grid = dim3((unsigned)std::max<int64_t>(1, std::min<int64_t>(need, (int64_t)h->sm_count * occ)));
+  kl.block = dim3((unsigned)(fiss::kRecWarps * 32));
+  kl.smem = smem;
+  kl.pdl = a.after_producer != 0;
+  kl.push(a);
   return issue(h, st, kl);
 }
 
@@ -1110,7 +1135,13 @@ int32_t fiss_pick_winners_dev(fiss_handle* h, void* stream, const double* d_ego,
     lp.a.mat = nullptr;
     lp.a.records = d_records;
     lp.a.n_stride = n_stride;
-    return launch_eval<false, true>(h, st, lp, 2);
+    lp.a.total = B;
+    static const bool list_records = std::getenv("FISS_LIST_RECORDS") != nullptr;  // A/B: the generic one-warp-per-problem kernel
+    if (list_records) return launch_eval<false, true>(h, st, lp, 2);
+    // warps per problem: one pass over the steps (2 covers the 50-step horizons, 4 the 100-step ones)
+    if (n_stride <= 32) return launch_record<1>(h, st, lp.a, 5);
+    if (n_stride <= 64) return launch_record<2>(h, st, lp.a, 7);
+    return launch_record<4>(h, st, lp.a, 8);
   }
   return FISS_OK;
 }
