@@ -179,6 +179,7 @@ struct fiss_handle {
   std::vector<double> end_cache;
   // product lattice (fiss_grid): device axes [4][kAxisMax] + the expanded [C][4] table in d_end
   DevBuf d_axes;
+  DevBuf d_work;   // work counters of the lattice kernel (zero between launches)
   DevBuf d_fit_in, d_fit_out;  // fiss_fit_splines_host / fiss_frame_samples_host
   cudaStream_t capture_stream = nullptr;       // graph_run: launches are captured here when a graph is (re)built
   cudaStream_t copy_stream = nullptr;          // plan_common: D2H of one half of a big batch under the other half's kernels
@@ -723,7 +724,21 @@ int32_t eval_grid(fiss_handle* h, cudaStream_t st, const double* d_ego, int B, c
     }
     break;
   }
-  a.items = ((base_items + a.slots - 1) / a.slots) * a.n_chunks;
+  // Work items (handed out through a device counter, big ones first): FISS_BIG_FRAC percent of the pairs travel in items of
+  // `slots` pairs, the rest one pair per item, so that the CTAs run out of work together.
+  // (A/B switches: FISS_DYN_MAT / FISS_DYN = 0 | 1 for the materialising / winner-only kernel, FISS_BIG_FRAC = percent.)
+  static const int big_pct = std::getenv("FISS_BIG_FRAC") ? std::max(0, std::min(100, std::atoi(std::getenv("FISS_BIG_FRAC")))) : 70;
+  static const bool dyn_mat = std::getenv("FISS_DYN_MAT") ? std::atoi(std::getenv("FISS_DYN_MAT")) != 0 : false;
+  static const bool dyn_win = std::getenv("FISS_DYN") ? std::atoi(std::getenv("FISS_DYN")) != 0 : true;
+  a.dynamic = (yaw ? dyn_mat : dyn_win) && a.n_chunks == 1 && a.slots > 1;
+  if (a.n_chunks == 1) {
+    a.n_big = a.dynamic ? (int32_t)(base_items * big_pct / 100 / a.slots) : (int32_t)((base_items + a.slots - 1) / a.slots);
+    a.items = a.dynamic ? a.n_big + (base_items - (int64_t)a.n_big * a.slots) : a.n_big;
+  } else {
+    a.n_big = 0;
+    a.items = base_items * a.n_chunks;
+  }
+  a.work = h->d_work.as<uint32_t>();  // (allocated and zeroed by fiss_create)
   const int warps = std::max(1, std::min(fiss::grid_warps(yaw), a.slots * std::max(g->nv + a.d_chunk, a.d_chunk * g->nv)));
   if (L.bytes > kSmemLimit)
     return fail(h, FISS_ERR_CAPACITY,
@@ -749,6 +764,18 @@ int32_t fiss_debug_phase_cycles(long long* out) {
   long long zero[16] = {0};
   if (cudaMemcpyFromSymbol(out, g_fiss_phase, 8 * sizeof(long long)) != cudaSuccess) return FISS_ERR_CUDA;
   if (cudaMemcpyToSymbol(g_fiss_phase, zero, sizeof(zero)) != cudaSuccess) return FISS_ERR_CUDA;
+  return FISS_OK;
+}
+#endif
+
+#ifdef FISS_TRACE
+// debug builds only (tools/warp_trace.py): copy out and clear the per-warp stage stamps of the lattice kernel
+int32_t fiss_debug_trace(long long* out, int64_t n) {
+  const size_t bytes = sizeof(long long) * (size_t)std::min<int64_t>(n, (int64_t)(sizeof(g_fiss_trace) / sizeof(long long)));
+  if (cudaMemcpyFromSymbol(out, g_fiss_trace, bytes) != cudaSuccess) return FISS_ERR_CUDA;
+  void* sym = nullptr;
+  if (cudaGetSymbolAddress(&sym, g_fiss_trace) != cudaSuccess) return FISS_ERR_CUDA;
+  if (cudaMemset(sym, 0, sizeof(g_fiss_trace)) != cudaSuccess) return FISS_ERR_CUDA;
   return FISS_OK;
 }
 #endif
@@ -782,6 +809,13 @@ int32_t fiss_create(int32_t device, fiss_handle** out) {
   if (!h) return fail(nullptr, FISS_ERR_CUDA, "out of host memory");
   h->device = device;
   h->sm_count = prop.multiProcessorCount;
+  // work counters of the lattice kernel: zero between launches (the last CTA of a launch clears them)
+  e = h->d_work.ensure(256);
+  if (e == cudaSuccess) e = cudaMemset(h->d_work.p, 0, 256);
+  if (e != cudaSuccess) {
+    delete h;
+    return fail(nullptr, FISS_ERR_CUDA, std::string("work counters: ") + cudaGetErrorString(e));
+  }
   *out = h;
   return FISS_OK;
 }
@@ -791,7 +825,7 @@ int32_t fiss_destroy(fiss_handle* h) {
   DeviceGuard device_guard_(h->device);
   for (DevBuf* b : {&h->spline, &h->obs_tab, &h->obs_const, &h->obs_raw, &h->obs_lw, &h->obs_valid, &h->d_ego,
                     &h->d_end, &h->d_cost, &h->d_flags, &h->d_best_idx, &h->d_best_cost, &h->d_meta, &h->d_records,
-                    &h->d_es, &h->d_axes, &h->d_fit_in, &h->d_fit_out, &h->d_arena})
+                    &h->d_es, &h->d_axes, &h->d_work, &h->d_fit_in, &h->d_fit_out, &h->d_arena})
     b->release();
   h->h_in.release();
   h->h_out.release();

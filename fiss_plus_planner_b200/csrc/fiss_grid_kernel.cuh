@@ -48,6 +48,17 @@ __device__ long long g_fiss_phase[16];
 #define FISS_PHASE(k) do { } while (0)
 #endif
 
+#ifdef FISS_TRACE
+// debug build only (tools/warp_trace.py): lane 0 of every warp stamps clock64() at the stage boundaries of its first
+// kTraceItems items -- [CTA][warp][item][stamp]; stamp 14 of item 0 is the kernel entry, stamp 15 the SM id
+constexpr int kTraceCtas = 512, kTraceWarps = 16, kTraceItems = 8, kTraceStamps = 16;
+__device__ long long g_fiss_trace[kTraceCtas * kTraceWarps * kTraceItems * kTraceStamps];
+#define FISS_STAMP(k) do { if ((threadIdx.x & 31) == 0 && trace_item < kTraceItems && blockIdx.x < kTraceCtas) \
+    g_fiss_trace[((blockIdx.x * kTraceWarps + (threadIdx.x >> 5)) * kTraceItems + trace_item) * kTraceStamps + (k)] = clock64(); } while (0)
+#else
+#define FISS_STAMP(k) do { } while (0)
+#endif
+
 // Output rows are written once and never read by the kernel: streaming stores (st.global.cs, evict-first) keep them
 // from displacing the tables and the spilled registers in L1 / L2.
 #ifdef FISS_PLAIN_STORES
@@ -96,7 +107,7 @@ constexpr int kMatRows = FISS_MAT_GROUP;  // lateral rows one materialisation ta
 // Shared-memory carve-up (byte offsets, 16-byte aligned), used by the host for the launch size too.
 struct GridLayout {
   uint32_t spline, oc, obs, bbox, bbox_key, axes, slot_d, slot_base, slot_off, lon, th, lat, lon_cost, lat_cost, dmax, lon_viol,
-      lon_ncart, lon_E, counters, pairs, cflags, masks, listed, near_list, bytes;
+      lon_ncart, lon_E, rowdesc, counters, pairs, cflags, masks, listed, near_list, bytes;
 };
 
 struct GridArgs {
@@ -108,7 +119,11 @@ struct GridArgs {
   int32_t d_chunk;     // lateral rows per work item
   int32_t n_chunks;
   int32_t slots;       // (ego, horizon) pairs per work item; > 1 only when the lateral axis is not chunked
-  int64_t items;       // ceil(B * nt / slots) * n_chunks
+  int64_t items;       // work items of the launch: n_big + (B * nt - n_big * slots) when the lateral axis is not chunked, else
+                       // B * nt * n_chunks
+  int32_t n_big;       // items [0, n_big) carry `slots` pairs each, the items behind them one pair (n_chunks == 1)
+  int32_t dynamic;     // 1: the items are handed out through the device counter `work`; 0: with a grid stride
+  uint32_t* work;      // [0] next item to hand out (minus gridDim.x), [1] CTAs that are done; both zero between launches
   int64_t total;       // B * C
   fiss_params p;
   const double* spline;  // [9][Kp]
@@ -162,7 +177,8 @@ __host__ __device__ inline GridLayout grid_layout(int Kp, int Mp, int E_stage, i
   L.lon_viol = o;   o += grid_align16(lon_rows * 4u);
   L.lon_ncart = o;  o += grid_align16(lon_rows * 4u);
   L.lon_E = o;      o += grid_align16(lon_rows * 4u);
-  L.counters = o;   o += 16;
+  L.rowdesc = o;    o += yaw ? lon_rows * 16u : 0u;  // per longitudinal row: what a materialisation task needs, one LDS.128
+  L.counters = o;   o += 32;
   L.pairs = o;      o += grid_align16(lon_rows * e_pad * 4u);
   L.cflags = o;     o += grid_align16(lat_rows * nv * 4u);
   L.masks = o;      o += grid_align16(lon_rows * e_pad * words * 4u);
@@ -270,7 +286,7 @@ __device__ __forceinline__ void mat_rows(const GridArgs& a, const MatOut& mo, co
       FISS_ST(o + 4 * a.mat_pitch, kap[r]);
     }
   }
-  if (a.kap_limit < CUDART_INF) {  // the optional curvature mask is on (uniform over the launch; NaN never exceeds)
+  if (a.p.check_curvature) {  // the optional curvature mask is on (uniform over the launch; NaN never exceeds)
 #pragma unroll
     for (int r = 0; r < R; ++r)
       if (fabs(kap[r]) > a.kap_limit) atomicOr(cf + r * nv, FISS_FLAG_CURVATURE);
@@ -283,6 +299,15 @@ __global__ void __launch_bounds__(grid_warps(kYaw) * 32, grid_min_ctas(kYaw)) fi
 #ifdef FISS_PHASE_TIMING
   long long phase_acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   long long phase_t = clock64();
+#endif
+#ifdef FISS_TRACE
+  int trace_item = 0;
+  FISS_STAMP(14);  // kernel entry
+  if ((threadIdx.x & 31) == 0 && blockIdx.x < kTraceCtas) {
+    unsigned smid;
+    asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+    g_fiss_trace[((blockIdx.x * kTraceWarps + (threadIdx.x >> 5)) * kTraceItems) * kTraceStamps + 15] = smid;
+  }
 #endif
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const GridLayout& L = a.lay;
@@ -306,10 +331,14 @@ __global__ void __launch_bounds__(grid_warps(kYaw) * 32, grid_min_ctas(kYaw)) fi
   uint32_t* lon_viol = reinterpret_cast<uint32_t*>(smem_raw + L.lon_viol);
   int32_t* lon_ncart = reinterpret_cast<int32_t*>(smem_raw + L.lon_ncart);
   int32_t* lon_E = reinterpret_cast<int32_t*>(smem_raw + L.lon_E);        // checked steps of the row
+  // (n', output offset of (slot, j) relative to the item's first candidate, cflags index of (slot, row 0, j), lat index of
+  // (slot, row 0, step 0)): written by the row warp, read once per materialisation task (kYaw)
+  int4* rowdesc = reinterpret_cast<int4*>(smem_raw + L.rowdesc);
   uint32_t* npairs = reinterpret_cast<uint32_t*>(smem_raw + L.counters);  // length of the work list
   uint32_t* n_near = npairs + 1;     // length of near_list
   uint32_t* rows_done = npairs + 2;  // longitudinal rows of the item that have folded their frame points into the boxes
   uint32_t* row_task = npairs + 3;   // next row task of stage A
+  uint32_t* next_item = npairs + 4;  // [2] the CTA's next work item, by item parity (fetched one item ahead)
   uint32_t* pairs = reinterpret_cast<uint32_t*>(smem_raw + L.pairs);      // (row << 16 | checked step) with any proximity bit
   uint32_t* cflags = reinterpret_cast<uint32_t*>(smem_raw + L.cflags);    // per candidate: collision / curvature bits
   uint32_t* masks = reinterpret_cast<uint32_t*>(smem_raw + L.masks);
@@ -379,8 +408,8 @@ __global__ void __launch_bounds__(grid_warps(kYaw) * 32, grid_min_ctas(kYaw)) fi
   const uint32_t n_chunks = (uint32_t)a.n_chunks, nt = (uint32_t)a.nt;
   const uint32_t n_bk = (uint32_t)a.B * nt;  // (ego, horizon) pairs of the launch
 
-  // Per-item state of stage A' / B: clear masks, list marks and counters.  Runs before the first item and inside stage C of every item (which is the only reader of cflags and
-  // clears them itself), so that an item costs one barrier less.
+  // Per-item state of stage A' / B: clear masks, list marks and counters.  Runs before the first item and inside stage C of
+  // every item (which is the only reader of cflags and clears them itself), so that an item costs one barrier less.
   auto reset_item_state = [&]() {
     if (threadIdx.x == 0) {
       *dmax_bits = 0u;
@@ -396,12 +425,28 @@ __global__ void __launch_bounds__(grid_warps(kYaw) * 32, grid_min_ctas(kYaw)) fi
   };
   // The slots of an item: ego state, horizon, step count, output ids -- fetched one item ahead (the global loads are
   // in flight while the previous item finishes), double-buffered by the parity of the CTA's item count.
+  // Work items: dealt with a grid stride, or (a.dynamic) handed out through a global counter -- the time of an item follows
+  // its collision stage, which varies with the scene around the ego state; the big items then come first and single pairs
+  // last, so that the CTAs run out of work together.
+  const uint32_t n_big = (uint32_t)a.n_big;
+  auto item_decode = [&](uint32_t item, uint32_t& bk0, uint32_t& chunk, int& Gv) {
+    if (n_chunks == 1u) {
+      const bool big = item < n_big;
+      bk0 = big ? item * (uint32_t)G : n_big * (uint32_t)G + (item - n_big);
+      Gv = big ? (int)min((uint32_t)G, n_bk - bk0) : 1;
+      chunk = 0u;
+    } else {
+      bk0 = item / n_chunks;
+      chunk = item - bk0 * n_chunks;
+      Gv = 1;
+    }
+  };
   auto load_slots = [&](uint32_t item, int par) {
     if (threadIdx.x < (unsigned)(8 * G) && item < n_items) {
       const int g = threadIdx.x >> 3, q = threadIdx.x & 7;
-      const uint32_t iq = n_chunks == 1u ? item : item / n_chunks;
-      const uint32_t bk0 = iq * (uint32_t)G;
-      const uint32_t chunk = item - iq * n_chunks;
+      uint32_t bk0, chunk;
+      int Gv_;
+      item_decode(item, bk0, chunk, Gv_);
       const uint32_t bk = bk0 + (uint32_t)g;
       if (bk < n_bk) {
         const uint32_t b = nt == 1u ? bk : __umulhi(bk, a.nt_magic), k = bk - b * nt;
@@ -428,11 +473,11 @@ __global__ void __launch_bounds__(grid_warps(kYaw) * 32, grid_min_ctas(kYaw)) fi
   FISS_PHASE(0);
 
   int par = 0;
-  for (uint32_t item = blockIdx.x; item < n_items; item += gridDim.x, par ^= 1) {
-    const uint32_t iq = n_chunks == 1u ? item : item / n_chunks;
-    const uint32_t bk0 = iq * (uint32_t)G;
-    const int chunk = (int)(item - iq * n_chunks);
-    const int Gv = (int)min((uint32_t)G, n_bk - bk0);  // slots of this item (the last item may be short)
+  for (uint32_t item = blockIdx.x; item < n_items; item = next_item[par ^ 1], par ^= 1) {
+    uint32_t bk0, chunk_u;
+    int Gv;  // slots of this item
+    item_decode(item, bk0, chunk_u, Gv);
+    const int chunk = (int)chunk_u;
     const int i0 = chunk * dc;
     const int rows_i = min(dc, a.nd - i0);
     const int n_lon = Gv * nv;
@@ -441,13 +486,21 @@ __global__ void __launch_bounds__(grid_warps(kYaw) * 32, grid_min_ctas(kYaw)) fi
     // the per-item state was reset before the loop / by the previous item's stage C, which also fetched this item's
     // slots; this barrier also means the previous item's readers are done with the tables
     __syncthreads();
-    // last item of this CTA: a dependent launch (the record kernel, fiss_pick_winners_dev) may start staging its tables
-    if (item + gridDim.x >= n_items) pdl_launch_dependents();
-#ifndef FISS_LATE_SLOTS
-    // the next item's slots: the other buffer is free from here on, and the global loads complete under stage A (issued
-    // at the end of stage C, their latency was exposed at this barrier)
-    load_slots(item + gridDim.x, par ^ 1);
-#endif
+    // Warp 0 draws the CTA's next item (the first one is blockIdx.x) and fetches its slots: the other buffer is free from
+    // here on, and the global loads complete under stage A.  Everybody reads next_item[] at the end of the item, four
+    // barriers from here.
+    if (warp == 0) {
+      uint32_t nxt = item + gridDim.x;
+      if (a.dynamic) {
+        if (lane == 0) nxt = gridDim.x + atomicAdd(&a.work[0], 1u);
+        nxt = __shfl_sync(kFull, nxt, 0);
+      }
+      if (lane == 0) next_item[par ^ 1] = nxt;
+      // last item of this CTA: a dependent launch (the record kernel, fiss_pick_winners_dev) may start staging its tables
+      if (nxt >= n_items) pdl_launch_dependents();
+      load_slots(nxt, par ^ 1);  // (threads < 8 * slots: all in warp 0)
+    }
+    FISS_STAMP(0);
     FISS_PHASE(1);
 
     // ---- stage A: one warp per row, rows dealt dynamically (the longitudinal rows, ~3x the work of a lateral row,
@@ -535,11 +588,17 @@ __global__ void __launch_bounds__(grid_warps(kYaw) * 32, grid_min_ctas(kYaw)) fi
           lon_viol[jj] = viol;
           lon_ncart[jj] = n_cart;
           lon_E[jj] = E_row;
+          if (kYaw)
+            rowdesc[jj] = make_int4(n_cart, slot_off[par * kMaxSlots + g] + j * (a.sv * a.n_stride), g * dc * nv + j, g * dc * n_pad);
         }
         // frame points from the truncation on (and the pad) are NaN: the materialisation reads them without a test and
-        // x, y, heading and curvature of the steps outside the Cartesian part come out NaN by propagation
+        // x, y, heading and curvature of the steps outside the Cartesian part come out NaN by propagation; the speed row is
+        // NaN from its own length n on (the output rows are NaN-padded up to n_stride)
         if (kYaw)
-          for (int m = n_cart + lane; m < n_pad; m += 32) P2[base + m] = make_double2(CUDART_NAN, CUDART_NAN);
+          for (int m = n_cart + lane; m < n_pad; m += 32) {
+            P2[base + m] = make_double2(CUDART_NAN, CUDART_NAN);
+            if (m >= n) SD[base + m] = CUDART_NAN;
+          }
         // this row's frame points into the per-step bounding boxes of stage A' (min / max commute, so the boxes do not
         // depend on the order the rows arrive in)
         __syncwarp();
@@ -614,7 +673,9 @@ __global__ void __launch_bounds__(grid_warps(kYaw) * 32, grid_min_ctas(kYaw)) fi
         }
       }
     }
+    FISS_STAMP(1);
     __syncthreads();
+    FISS_STAMP(2);
     FISS_PHASE(2);
 
     // ---- stage A': proximity masks.  masks[jj][e] gets a bit per obstacle whose centre is within
@@ -654,7 +715,9 @@ __global__ void __launch_bounds__(grid_warps(kYaw) * 32, grid_min_ctas(kYaw)) fi
           }
         }
       }
+      FISS_STAMP(3);
       __syncthreads();
+      FISS_STAMP(4);
       FISS_PHASE(4);
       const uint32_t n_cand_pairs = *n_near * (uint32_t)n_lon;
       for (uint32_t q = threadIdx.x; q < n_cand_pairs; q += blockDim.x) {
@@ -674,7 +737,9 @@ __global__ void __launch_bounds__(grid_warps(kYaw) * 32, grid_min_ctas(kYaw)) fi
         }
       }
     }
+    FISS_STAMP(5);
     __syncthreads();
+    FISS_STAMP(6);
     FISS_PHASE(5);
 
     // ---- stage B, collision (has_collision, frenet_optimal_planner.py:168-195): one lane per
@@ -735,6 +800,7 @@ __global__ void __launch_bounds__(grid_warps(kYaw) * 32, grid_min_ctas(kYaw)) fi
     __syncthreads();
     FISS_PHASE(6);
 #endif
+    FISS_STAMP(7);
     // ---- stage B, materialisation (calc_global_paths, frenet_optimal_planner.py:121-134).
     // Lanes = flattened (longitudinal row jj, time step m) elements f = jj*n_stride + m of the frame tables, cut into
     // blocks of 31 outputs: the 32nd lane of a block only supplies the heading of the next step (kappa_m needs
@@ -752,7 +818,6 @@ __global__ void __launch_bounds__(grid_warps(kYaw) * 32, grid_min_ctas(kYaw)) fi
       // (the host checks that slots * C * n_stride < 2^31 elements)
       mo.f_x = a.mat ? a.mat + slot_base[par * kMaxSlots] * ns : nullptr;
       const int lat_pitch = a.sd * ns;
-      const int lon_pitch = a.sv * ns;
       // tasks t = blk * n_groups + grp.  A task recomputes its lane set-up from t (~35 issue slots against ~400 for its
       // rows): state carried from task to task was spilled to local memory, and the loads of the spilled loop state
       // were the longest stalls of the kernel.
@@ -765,16 +830,15 @@ __global__ void __launch_bounds__(grid_warps(kYaw) * 32, grid_min_ctas(kYaw)) fi
         const int f = blk * 31 + lane;
         const int jj = min((int)(((uint32_t)f * ns_magic) >> 20), n_lon - 1);
         const int m = f - jj * ns;  // >= ns for the lanes past the end of the table
-        const int g = (int)(((uint32_t)jj * nv_magic) >> 20);
-        const int j = jj - g * nv;
-        const int n = (int)sl[8 * g + 7];
-        const int n_cart = lon_ncart[jj];
+        const int4 rd = rowdesc[jj];  // (n', output offset, cflags index, lat index) of the row
+        const int n_cart = rd.x;
         const bool in_cart = m < n_cart;  // (n' <= n <= ns)
         // yaw_m = atan2 of segment min(m, n'-2): the last point repeats the previous heading (:127-130).  Steps
         // outside the Cartesian part read NaN frame points (stage A), and so does the neighbour of a lone point
         // (n' == 1: yaw / ds / c stay empty, :121).
         const int seg = in_cart ? max(min(m, n_cart - 2), 0) : min(m, n_pad - 2);
-        const double2* fp = P2 + jj * n_pad + seg;
+        const int sidx = jj * n_pad + seg;
+        const double2* fp = P2 + sidx;
         mo.has_seg = in_cart && n_cart >= 2;
         mo.at_seg = m == seg;
         mo.has_kap = m < n_cart - 1 && lane < 31;  // lane 31 only supplies the next heading
@@ -782,15 +846,14 @@ __global__ void __launch_bounds__(grid_warps(kYaw) * 32, grid_min_ctas(kYaw)) fi
 #ifdef FISS_EXP_NOSTORE
         mo.writes = mo.writes && a.B < 0;
 #endif
-        const double sd_v = m < n ? SD[jj * n_pad + min(m, n_pad - 1)] : CUDART_NAN;
+        const double sd_v = SD[sidx - seg + min(m, n_pad - 1)];  // NaN from the row's length on (stage A)
         const double2 Pa = fp[0], Pb = fp[1];
         const double2 Ua = fp[row_len], Ub = fp[row_len + 1];  // U2 = P2 + row_len
-        const double th = TH[jj * n_pad + seg];
+        const double th = TH[sidx];
         const int i_first = grp * kMatRows;
-        const int ll = g * dc + i_first;  // first lateral row of the group in the lane's slot
-        const double* Dr = lat + ll * n_pad + seg;
-        const int off = slot_off[par * kMaxSlots + g] + i_first * lat_pitch + j * lon_pitch + m;
-        uint32_t* cf = cflags + ll * nv + j;
+        const double* Dr = lat + (rd.w + i_first * n_pad + seg);  // first lateral row of the group in the lane's slot
+        const int off = rd.y + i_first * lat_pitch + m;
+        uint32_t* cf = cflags + (rd.z + i_first * nv);
         const int rows_here = min(kMatRows, rows_i - i_first);  // warp-uniform
         int r = 0;
         for (; r + kMatIlp <= rows_here; r += kMatIlp)
@@ -799,7 +862,9 @@ __global__ void __launch_bounds__(grid_warps(kYaw) * 32, grid_min_ctas(kYaw)) fi
           mat_rows<1>(a, mo, Pa, Ua, Pb, Ub, th, sd_v, Dr + r * n_pad, n_pad, off + r * lat_pitch, lat_pitch, cf + r * nv, nv);
       }
     }
+    FISS_STAMP(8);
     __syncthreads();
+    FISS_STAMP(9);
     FISS_PHASE(7);
 
     // ---- stage C: one lane per candidate -- cost (cost_function.py:41-50) and the flags word; then the reset of the
@@ -826,9 +891,18 @@ __global__ void __launch_bounds__(grid_warps(kYaw) * 32, grid_min_ctas(kYaw)) fi
         a.flags[out_id] = viol | extra | ((uint32_t)n_cart << FISS_FLAG_NCART_SHIFT);
       }
       reset_item_state();
-#ifdef FISS_LATE_SLOTS
-      load_slots(item + gridDim.x, par ^ 1);
+    }
+    FISS_STAMP(10);
+#ifdef FISS_TRACE
+    ++trace_item;
 #endif
+  }
+  // every CTA has drawn its last (out-of-range) item by now: the last one to leave zeroes the counters for the next launch
+  if (threadIdx.x == 0 && a.dynamic) {
+    __threadfence();
+    if (atomicAdd(&a.work[1], 1u) == gridDim.x - 1u) {
+      a.work[0] = 0u;
+      a.work[1] = 0u;
     }
   }
 #ifdef FISS_PHASE_TIMING

@@ -184,7 +184,6 @@ __device__ __forceinline__ void segment_frame_n(const double (&dx)[R], const dou
     a[i] = fma(dx[i], ux, dy[i] * uy);
     b[i] = fma(dy[i], ux, -(dx[i] * uy));
     h2[i] = fma(dx[i], dx[i], dy[i] * dy[i]);
-    narrow = narrow && (fabs(b[i]) <= kNarrow * a[i]);  // false for a < 0 and for NaN
   }
   // q = b / a: reciprocal seed (~2^-20) + one cubic Newton step (~2^-60)
 #pragma unroll
@@ -218,11 +217,15 @@ __device__ __forceinline__ void segment_frame_n(const double (&dx)[R], const dou
   for (int i = 0; i < R; ++i) pe[i] = fma(u[i], po[i], pe[i]);
 #pragma unroll
   for (int i = 0; i < R; ++i) po[i] = q[i] * u[i];
+  // Range tests on the high words (integer pipe; the FP64 pipe is what this stage is short of).  narrow: a is a positive
+  // normal number and |q| < 0.29999995 (q is NaN when a is: not narrow).  outside: |yaw| >= 3.1415926218 -- a
+  // conservative "may have left (-pi, pi]" (NaN / Inf of a lane without a segment excluded); the selects below are exact.
   bool outside = false;
 #pragma unroll
   for (int i = 0; i < R; ++i) {
     yaw[i] = th + fma(po[i], pe[i], q[i]);
-    outside = outside || fabs(yaw[i]) > 3.141592653589793;  // (false for the NaN of a lane without a segment)
+    narrow = narrow && __double2hiint(a[i]) >= 0x00100000 && (uint32_t)(__double2hiint(q[i]) & 0x7fffffff) < 0x3fd33333u;
+    outside = outside || ((uint32_t)(__double2hiint(yaw[i]) & 0x7fffffff) - 0x400921fbu) < (0x7ff00000u - 0x400921fbu);
   }
   // th is in (-pi, pi] and |atan(q)| < 0.3: the sum leaves that range only where the road itself points (almost) along
   // -x -- one warp-uniform vote keeps the two selects per segment off the common path
