@@ -420,17 +420,27 @@ def run_ours(args):
         return float(t.item())
 
     def timed_steps(fn):
-        """K steps between two events (the headline) with one event after every step (the per-step spread)."""
+        """K steps between two events (the headline): nothing but the steps' own launches sits on the stream between them,
+        so that consecutive steps chain (the next step's CTAs start on the SMs this step's last items leave idle --
+        programmatic dependent launch, fiss_abi.cu eval_grid).  Then the same K steps once more with an event after every
+        step: the per-step spread (an event between two steps serialises them: the median of that pass is the time of a
+        step ON ITS OWN)."""
         for _ in range(args.warmup):
             fn()
         barrier()
+        t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0.record(stream)
+        for i in range(args.steps):
+            fn()
+        t1.record(stream)
+        barrier()
+        total = t0.elapsed_time(t1)
         marks = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
         marks[0].record(stream)
         for i in range(args.steps):
             fn()
             marks[i + 1].record(stream)
         barrier()
-        total = marks[0].elapsed_time(marks[-1])
         per = [marks[i].elapsed_time(marks[i + 1]) for i in range(args.steps)]
         return max_over_ranks(total), max_over_ranks(float(np.median(per)))
 
@@ -438,12 +448,21 @@ def run_ours(args):
     time.sleep(0.5 if rank == 0 else 0.0)     # let the sampler's start-up pass
     launches0 = eng.launch_count
     total_ms, median_ms = timed_steps(step_device)
-    launches = (eng.launch_count - launches0) * args.steps // (args.steps + args.warmup)
+    launches = (eng.launch_count - launches0) * args.steps // (2 * args.steps + args.warmup)   # (warm-up + the two timed passes)
 
-    # ---- the lattice kernel alone (roofline): CUDA events around every launch, same buffers
+    # ---- the lattice kernel alone (roofline), same buffers: (a) K launches between two events -- its average launch
+    # duration as it runs in the step loop, consecutive launches chained; (b) CUDA events around every launch -- a launch on
+    # its own (the events serialise the launches)
     for _ in range(args.warmup):
         eng.eval_grid_dev(ego_t, grid, prm, cost_t, flags_t, mat_t, n_stride, stream=sptr)
     barrier()
+    t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0.record(stream)
+    for i in range(args.steps):
+        eng.eval_grid_dev(ego_t, grid, prm, cost_t, flags_t, mat_t, n_stride, stream=sptr)
+    t1.record(stream)
+    barrier()
+    kern_ms = t0.elapsed_time(t1) / args.steps
     k_ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     for i in range(args.steps):
         k_ev[i][0].record(stream)
@@ -451,7 +470,7 @@ def run_ours(args):
         k_ev[i][1].record(stream)
     barrier()
     k_times = [a.elapsed_time(b) for a, b in k_ev]
-    kern_ms, kern_median_ms = float(np.mean(k_times)), float(np.median(k_times))
+    kern_alone_ms, kern_median_ms = float(np.mean(k_times)), float(np.median(k_times))
 
     # ---- winner-only mode (what plan() strictly needs; reported beside the headline)
     wo_ms, wo_median_ms = timed_steps(lambda: step_device(None))
@@ -561,7 +580,11 @@ def run_ours(args):
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic, "traffic_source": traffic_src,
                          "kernel": "fiss_grid_kernel<yaw> (materialising)", "kernel_ms": kern_ms,
-                         "kernel_ms_median": kern_median_ms,
+                         "kernel_ms_how": "average launch duration over a train of `steps` launches between two CUDA events "
+                                          "(consecutive launches chained by programmatic dependent launch, as in the step loop)",
+                         "kernel_ms_alone": kern_alone_ms, "kernel_ms_alone_median": kern_median_ms,
+                         "kernel_ms_alone_how": "CUDA events around every single launch (the events serialise the launches)",
+                         "frac_alone": alg / (kern_alone_ms * 1e-3) / 1e9 / peak,
                          "algorithmic_bytes_per_launch": alg, "peak_source": peak_src,
                          "note": "FP64-issue bound by arithmetic (SURVEY 8(d)); see profiles/ for ncu fp64 pipe utilisation"},
             "plan_cycle_p50_ms": p50,

@@ -179,7 +179,11 @@ struct fiss_handle {
   std::vector<double> end_cache;
   // product lattice (fiss_grid): device axes [4][kAxisMax] + the expanded [C][4] table in d_end
   DevBuf d_axes;
-  DevBuf d_work;   // work counters of the lattice kernel (zero between launches)
+  DevBuf d_work;   // work counters of the lattice kernel (zero between launches), two pairs
+  int work_parity = 0;
+  uint32_t lattice_seq = 0;  // lattice launches issued on this handle (chained launches)
+  int lattice_chained = 0;   // ... and whether the last one was chained (1: winner-only kernel, 2: materialising)
+  DevBuf d_shadow;           // chained launches: the first items' cost / flags, per CTA, two sets
   DevBuf d_fit_in, d_fit_out;  // fiss_fit_splines_host / fiss_frame_samples_host
   cudaStream_t capture_stream = nullptr;       // graph_run: launches are captured here when a graph is (re)built
   cudaStream_t copy_stream = nullptr;          // plan_common: D2H of one half of a big batch under the other half's kernels
@@ -387,7 +391,17 @@ int32_t launch_record(fiss_handle* h, cudaStream_t st, const fiss::EvalArgs& a, 
   const int64_t need = (a.total + per_cta - 1) / per_cta;
   KernelLaunch kl;
   kl.func = (const void*)kern;
-  kl.grid = dim3((unsigned)std::max<int64_t>(1, std::min<int64_t>(need, (int64_t)h->sm_count * occ)));
+  int64_t ctas = std::min<int64_t>(need, (int64_t)h->sm_count * occ);
+  // Behind a CHAINED lattice launch (eval_grid) the record kernel's CTAs take SM slots as that launch's CTAs retire and sit
+  // there until it is over, and the next step's lattice kernel cannot be scheduled before every record CTA is resident: a
+  // small record grid (it loops over the problems) leaves the retiring slots to the next step sooner.  Nobody waits for this
+  // kernel but the next step's second items and the next record kernel.  (FISS_REC_CTAS overrides.)
+  // Measured on the B200 (cfg4 step trains): 32 CTAs behind the materialising kernel (0.125 -> 0.108 ms per step; 128: 0.121),
+  // 64 behind the winner-only kernel (0.068 -> 0.058; 32: 0.065, 128: 0.060).
+  static const int rec_cap = std::getenv("FISS_REC_CTAS") ? std::max(1, std::atoi(std::getenv("FISS_REC_CTAS"))) : 0;
+  if (a.after_producer && h->record == nullptr && h->lattice_chained)
+    ctas = std::min<int64_t>(ctas, rec_cap > 0 ? rec_cap : (h->lattice_chained == 2 ? 32 : 64));
+  kl.grid = dim3((unsigned)std::max<int64_t>(1, ctas));
   kl.block = dim3((unsigned)(fiss::kRecWarps * 32));
   kl.smem = smem;
   kl.pdl = a.after_producer != 0;
@@ -638,6 +652,7 @@ int32_t launch_grid(fiss_handle* h, cudaStream_t st, const fiss::GridArgs& a, si
   kl.grid = dim3((unsigned)grid);
   kl.block = dim3((unsigned)threads);
   kl.smem = smem;
+  kl.pdl = a.chained != 0;
   kl.push(a);
   return issue(h, st, kl);
 }
@@ -724,21 +739,49 @@ int32_t eval_grid(fiss_handle* h, cudaStream_t st, const double* d_ego, int B, c
     }
     break;
   }
-  // Work items (handed out through a device counter, big ones first): FISS_BIG_FRAC percent of the pairs travel in items of
-  // `slots` pairs, the rest one pair per item, so that the CTAs run out of work together.
-  // (A/B switches: FISS_DYN_MAT / FISS_DYN = 0 | 1 for the materialising / winner-only kernel, FISS_BIG_FRAC = percent.)
-  static const int big_pct = std::getenv("FISS_BIG_FRAC") ? std::max(0, std::min(100, std::atoi(std::getenv("FISS_BIG_FRAC")))) : 70;
-  static const bool dyn_mat = std::getenv("FISS_DYN_MAT") ? std::atoi(std::getenv("FISS_DYN_MAT")) != 0 : false;
+  // Chained launches (direct launches of batches that fill the GPU; FISS_CHAIN=0 switches it off): the lattice kernel is
+  // launched as a programmatic dependent of the previous kernel of the stream, so that its CTAs fill the SMs the previous
+  // step's last items leave idle (GridArgs::chained says what it waits for before it writes).  Two launches can then be
+  // drawing work items at the same time: the counters alternate between two pairs.
+  static const bool chain_on = std::getenv("FISS_CHAIN") ? std::atoi(std::getenv("FISS_CHAIN")) != 0 : true;
+  a.chained = chain_on && h->record == nullptr && a.n_chunks == 1;
+  // Work items: dealt with a grid stride, or handed out through a device counter in index order -- then FISS_BIG_FRAC percent
+  // of the pairs travel in items of `slots` pairs and the rest one pair per item, so that the CTAs run out of work together
+  // (tools/warp_trace.py: the time of an item follows its collision stage, which varies ~5x with the traffic around the ego
+  // state).  Measured on the B200 (cfg4): the winner-only kernel gains 4-5 % (e2e +4-8 %) at 70 %.  The materialising
+  // kernel on its own loses 2-5 % (single pairs cost it more than the even finish wins) and keeps the static deal -- but
+  // in a CHAINED launch its CTAs start at different times (as the previous step's CTAs retire) and must draw their work:
+  // with the static deal a late starter still has three items to do and the step loop falls back to one step after the
+  // other.  A/B switches: FISS_DYN / FISS_DYN_MAT = 0 | 1 for the winner-only / materialising kernel, FISS_BIG_FRAC = percent.
+  static const bool big_forced = std::getenv("FISS_BIG_FRAC") != nullptr;
+  static const int big_env = big_forced ? std::max(0, std::min(100, std::atoi(std::getenv("FISS_BIG_FRAC")))) : 70;
+  static const bool dyn_mat_forced = std::getenv("FISS_DYN_MAT") != nullptr;
+  static const bool dyn_mat = dyn_mat_forced ? std::atoi(std::getenv("FISS_DYN_MAT")) != 0 : false;
   static const bool dyn_win = std::getenv("FISS_DYN") ? std::atoi(std::getenv("FISS_DYN")) != 0 : true;
-  a.dynamic = (yaw ? dyn_mat : dyn_win) && a.n_chunks == 1 && a.slots > 1;
+  const bool can_deal = a.n_chunks == 1 && a.slots > 1;
+  a.dynamic = can_deal && (yaw ? (dyn_mat_forced ? dyn_mat : a.chained != 0) : dyn_win);
+  const int big_pct = big_forced ? big_env : (yaw ? 100 : 70);
+  const int64_t full_items = (base_items + a.slots - 1) / a.slots;
   if (a.n_chunks == 1) {
-    a.n_big = a.dynamic ? (int32_t)(base_items * big_pct / 100 / a.slots) : (int32_t)((base_items + a.slots - 1) / a.slots);
-    a.items = a.dynamic ? a.n_big + (base_items - (int64_t)a.n_big * a.slots) : a.n_big;
+    const bool split = a.dynamic && big_pct < 100;
+    a.n_big = split ? (int32_t)(base_items * big_pct / 100 / a.slots) : (int32_t)full_items;
+    a.items = split ? a.n_big + (base_items - (int64_t)a.n_big * a.slots) : a.n_big;
   } else {
     a.n_big = 0;
     a.items = base_items * a.n_chunks;
   }
-  a.work = h->d_work.as<uint32_t>();  // (allocated and zeroed by fiss_create)
+  a.seq = ++h->lattice_seq;
+  h->lattice_chained = a.chained ? (yaw ? 2 : 1) : 0;
+  a.shadow = nullptr;
+  a.shadow_stride = (a.slots * a.d_chunk * a.nv + 1) & ~1;
+  if (a.chained) {  // shadow blocks for the first items' cost / flags: one per resident CTA, two sets
+    const size_t set_bytes = (size_t)h->sm_count * 8 * a.shadow_stride * 20;  // (<= 8 resident CTAs per SM)
+    FISS_CUDA(h, h->d_shadow.ensure(2 * set_bytes));
+    a.shadow = h->d_shadow.as<unsigned char>() + (size_t)(a.seq & 1u) * set_bytes;
+  }
+  h->work_parity ^= 1;
+  a.work = h->d_work.as<uint32_t>() + 2 * h->work_parity;  // (allocated and zeroed by fiss_create)
+  a.work_done = h->d_work.as<uint32_t>() + 4;
   const int warps = std::max(1, std::min(fiss::grid_warps(yaw), a.slots * std::max(g->nv + a.d_chunk, a.d_chunk * g->nv)));
   if (L.bytes > kSmemLimit)
     return fail(h, FISS_ERR_CAPACITY,
@@ -825,7 +868,7 @@ int32_t fiss_destroy(fiss_handle* h) {
   DeviceGuard device_guard_(h->device);
   for (DevBuf* b : {&h->spline, &h->obs_tab, &h->obs_const, &h->obs_raw, &h->obs_lw, &h->obs_valid, &h->d_ego,
                     &h->d_end, &h->d_cost, &h->d_flags, &h->d_best_idx, &h->d_best_cost, &h->d_meta, &h->d_records,
-                    &h->d_es, &h->d_axes, &h->d_work, &h->d_fit_in, &h->d_fit_out, &h->d_arena})
+                    &h->d_es, &h->d_axes, &h->d_work, &h->d_shadow, &h->d_fit_in, &h->d_fit_out, &h->d_arena})
     b->release();
   h->h_in.release();
   h->h_out.release();
@@ -1419,7 +1462,11 @@ int32_t fiss_plan_grid_dev(fiss_handle* h, void* stream, const double* d_ego, in
   rc = ensure_grid(h, st, g, p, &n_max);
   if (rc != FISS_OK) return rc;
   const int C = g->nd * g->nv * g->nt;
-  const bool as_graph = graphs_enabled();
+  // A batch that fills the GPU is issued launch by launch, so that consecutive steps chain (see eval_grid: the next step's
+  // CTAs start on the SMs this step's last items leave idle); a small one -- launch-latency bound -- as one graph launch.
+  static const bool chain_on = std::getenv("FISS_CHAIN") ? std::atoi(std::getenv("FISS_CHAIN")) != 0 : true;
+  const bool fills_gpu = (int64_t)B * g->nt >= 2 * (int64_t)h->sm_count;
+  const bool as_graph = graphs_enabled() && !(chain_on && fills_gpu);
   std::vector<KernelLaunch> kl;
   if (as_graph) h->record = &kl;
   rc = eval_grid(h, st, d_ego, B, g, n_max, p, d_cost, d_flags, d_mat, n_stride);

@@ -123,7 +123,25 @@ struct GridArgs {
                        // B * nt * n_chunks
   int32_t n_big;       // items [0, n_big) carry `slots` pairs each, the items behind them one pair (n_chunks == 1)
   int32_t dynamic;     // 1: the items are handed out through the device counter `work`; 0: with a grid stride
-  uint32_t* work;      // [0] next item to hand out (minus gridDim.x), [1] CTAs that are done; both zero between launches
+  // Chained launches: the kernel is launched as a programmatic dependent of the previous kernel of the stream (normally the
+  // previous step's record kernel, itself a dependent of the previous lattice launch), so that the CTAs of this launch fill
+  // the SMs that the previous launch's last items leave idle.  Inputs are read-only; before a CTA's first OUTPUT write the
+  // earlier launches must be out of the way:
+  //   materialised rows  the previous lattice launch may still be writing the same buffer: wait until its last CTA has
+  //                      published `seq - 1` in work[4] (every lattice launch publishes its sequence number when all its CTAs
+  //                      are done -- it is running or finished by the time a CTA of this launch exists, so the wait ends);
+  //   cost / flags       the previous step's record kernel reads them: griddepcontrol.wait (the whole previous kernel) --
+  //                      but not before the CTA's SECOND item: the first item's values go to a shadow block of the engine
+  //                      (`shadow`: per CTA ids, costs, flags; two blocks alternate between launches) and are copied
+  //                      into the volume behind the wait, by which time that kernel is long over.
+  int32_t chained;
+  unsigned char* shadow;   // [gridDim.x][shadow_stride * 20 B]
+  int32_t shadow_stride;   // entries per CTA (>= candidates of an item)
+  uint32_t seq;        // sequence number of this lattice launch on its handle
+  uint32_t* work;      // [0] next item to hand out (minus gridDim.x), [1] CTAs that are done (both zero between launches;
+                       // two such pairs alternate between launches: [0..1], [2..3]); [4] sequence number of the last
+                       // lattice launch all of whose CTAs are done (work_done points at it)
+  uint32_t* work_done;
   int64_t total;       // B * C
   fiss_params p;
   const double* spline;  // [9][Kp]
@@ -472,6 +490,20 @@ __global__ void __launch_bounds__(grid_warps(kYaw) * 32, grid_min_ctas(kYaw)) fi
   __syncthreads();
   FISS_PHASE(0);
 
+  bool chain_waited = false, mat_gate_open = false;
+  // shadow block of this CTA (chained launches): ids, costs, flags; the thread that wrote an entry copies it into the volume
+  int n_shadow = -1;  // entries in the shadow block (-1: the first item is still to come)
+  auto flush_shadow = [&]() {
+    int64_t* sh_id = reinterpret_cast<int64_t*>(a.shadow + (size_t)blockIdx.x * a.shadow_stride * 20);
+    double* sh_cost = reinterpret_cast<double*>(sh_id + a.shadow_stride);
+    uint32_t* sh_flags = reinterpret_cast<uint32_t*>(sh_cost + a.shadow_stride);
+    for (int cidx = threadIdx.x; cidx < n_shadow; cidx += blockDim.x) {
+      const int64_t id = sh_id[cidx];
+      a.cost[id] = sh_cost[cidx];
+      a.flags[id] = sh_flags[cidx];
+    }
+    n_shadow = 0;
+  };
   int par = 0;
   for (uint32_t item = blockIdx.x; item < n_items; item = next_item[par ^ 1], par ^= 1) {
     uint32_t bk0, chunk_u;
@@ -808,6 +840,18 @@ __global__ void __launch_bounds__(grid_warps(kYaw) * 32, grid_min_ctas(kYaw)) fi
     // lane loads its two frame points (4 x LDS.128) and advances the heading chains of the group's rows in lockstep
     // (mat_rows); five coalesced stores per row.
     if (kYaw) {
+      // first output write of this CTA (materialised rows): the previous launch -- which may still be writing the same
+      // buffers, or reading this launch's cost / flags volume -- has to be over
+      if (a.chained && !mat_gate_open) {
+        mat_gate_open = true;
+        if (lane == 0) {
+          uint32_t done;
+          do {
+            asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(done) : "l"(a.work_done) : "memory");
+          } while ((int32_t)(done - (a.seq - 1u)) < 0);
+        }
+        __syncwarp();
+      }
       const int ns = a.n_stride;
       const uint32_t ns_magic = a.ns_magic;  // f / ns for f < 2^20 / ns
       const int n_blocks = (n_lon * ns + 30) / 31;
@@ -867,10 +911,21 @@ __global__ void __launch_bounds__(grid_warps(kYaw) * 32, grid_min_ctas(kYaw)) fi
     FISS_STAMP(9);
     FISS_PHASE(7);
 
+    // chained launches: the first item's cost / flags go to the CTA's shadow block; from the second item on the volume is
+    // written directly, behind the wait for the previous kernel of the stream
+    const bool to_shadow = a.chained && !chain_waited && n_shadow < 0;
+    if (a.chained && !chain_waited && !to_shadow) {
+      pdl_wait_producer();
+      chain_waited = true;
+      flush_shadow();
+    }
     // ---- stage C: one lane per candidate -- cost (cost_function.py:41-50) and the flags word; then the reset of the
     // per-item state and the fetch of the next item's slots
     {
       const int n_cand = Gv * rows_i * nv;
+      int64_t* sh_id = reinterpret_cast<int64_t*>(a.shadow + (size_t)blockIdx.x * a.shadow_stride * 20);
+      double* sh_cost = reinterpret_cast<double*>(sh_id + a.shadow_stride);
+      uint32_t* sh_flags = reinterpret_cast<uint32_t*>(sh_cost + a.shadow_stride);
       for (int cidx = threadIdx.x; cidx < n_cand; cidx += blockDim.x) {
         const int lt = (int)(((uint32_t)cidx * nv_magic) >> 20);  // lateral row among the item's Gv * rows_i
         const int j = cidx - lt * nv;
@@ -887,9 +942,18 @@ __global__ void __launch_bounds__(grid_warps(kYaw) * 32, grid_min_ctas(kYaw)) fi
         // n' == 1 with obstacles: traj.yaw[0] raises inside the try => "collision" (:178-182)
         if (a.M > 0 && min(n_cart, t_left) > 0 && n_cart < 2 && (p.collide_all || viol == 0)) extra |= FISS_FLAG_COLLISION;
         const int64_t out_id = slot_base[par * kMaxSlots + g] + ii * a.sd + j * a.sv;
-        a.cost[out_id] = (cost_time + (lon_cost[jj] + lat_cost[ll])) * inv_n;
-        a.flags[out_id] = viol | extra | ((uint32_t)n_cart << FISS_FLAG_NCART_SHIFT);
+        const double cost_v = (cost_time + (lon_cost[jj] + lat_cost[ll])) * inv_n;
+        const uint32_t flags_v = viol | extra | ((uint32_t)n_cart << FISS_FLAG_NCART_SHIFT);
+        if (to_shadow) {
+          sh_id[cidx] = out_id;
+          sh_cost[cidx] = cost_v;
+          sh_flags[cidx] = flags_v;
+        } else {
+          a.cost[out_id] = cost_v;
+          a.flags[out_id] = flags_v;
+        }
       }
+      if (to_shadow) n_shadow = n_cand;
       reset_item_state();
     }
     FISS_STAMP(10);
@@ -897,12 +961,20 @@ __global__ void __launch_bounds__(grid_warps(kYaw) * 32, grid_min_ctas(kYaw)) fi
     ++trace_item;
 #endif
   }
-  // every CTA has drawn its last (out-of-range) item by now: the last one to leave zeroes the counters for the next launch
-  if (threadIdx.x == 0 && a.dynamic) {
+  if (a.chained && !chain_waited) {  // (a CTA with a single item)
+    pdl_wait_producer();
+    flush_shadow();
+  }
+  // Every CTA has drawn its last (out-of-range) item by now and its output writes are issued: the last one to leave zeroes
+  // the counters for the launch after the next and publishes this launch's sequence number (chained launches, above).
+  __syncthreads();
+  if (threadIdx.x == 0) {
     __threadfence();
     if (atomicAdd(&a.work[1], 1u) == gridDim.x - 1u) {
       a.work[0] = 0u;
       a.work[1] = 0u;
+      __threadfence();
+      asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(a.work_done), "r"(a.seq) : "memory");
     }
   }
 #ifdef FISS_PHASE_TIMING

@@ -46,6 +46,10 @@ __global__ void __launch_bounds__(kRecWarps * 32) fiss_record_kernel(const EvalA
     bulk_g2s(sp, a.spline, spline_bytes, bar);
   }
   mbar_wait(bar, 0);
+  // the next launch of the stream (the next step's lattice kernel, when it is launched as a programmatic dependent: chained
+  // launches, fiss_abi.cu eval_grid) may be scheduled: its CTAs take the SMs that this step's last items leave idle, and
+  // wait for this kernel before they write what it reads
+  pdl_launch_dependents();
   if (a.after_producer) pdl_wait_producer();  // the lattice kernel's cost / flags volume
   __syncthreads();
 
