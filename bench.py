@@ -95,6 +95,7 @@ def config_dict(n_gpus, batch_per_gpu):
 
 # ------------------------------------------------------------------------------------------------ CPU baseline
 REFERENCE_ROOT = "/root/reference"
+CPU_BLOCK = 6   # steps of one cycle of the CPU arm's sample (cpu_rate)
 _CPU = {}
 
 
@@ -162,7 +163,10 @@ def cpu_rate(sc, steps: int, warmup: int, budget_s: float, min_s: float = 5.0):
         t_begin = time.perf_counter()
         i = 0
         while True:
-            egos = [tuple(float(v) for v in sc.ego[(i * workers + w) % len(sc.ego)]) for w in range(workers)]
+            # the steps cycle through ONE fixed block of CPU_BLOCK x workers ego states, and whole cycles are timed: the
+            # time of a plan() varies ~2x with the traffic around the ego state, and two runs that sampled different ego
+            # states (this leg of the two arms, different --steps / --warmup) disagreed by 20 %
+            egos = [tuple(float(v) for v in sc.ego[((i % CPU_BLOCK) * workers + w) % len(sc.ego)]) for w in range(workers)]
             t0 = time.perf_counter()
             res = pool.map(_cpu_worker_plan, egos, chunksize=1)
             dt = time.perf_counter() - t0
@@ -172,9 +176,9 @@ def cpu_rate(sc, steps: int, warmup: int, budget_s: float, min_s: float = 5.0):
                 cands += sum(res)
             i += 1
             elapsed = time.perf_counter() - t_begin
-            if elapsed > budget_s and times:
+            if elapsed > budget_s and times and len(times) % CPU_BLOCK == 0:
                 break
-            if len(times) >= steps and sum(times) >= min_s:
+            if len(times) >= steps and sum(times) >= min_s and len(times) % CPU_BLOCK == 0:
                 break
     total = float(np.sum(times))
     what = ("the UNMODIFIED reference FrenetOptimalPlanner.plan() from /root/reference (commonroad symbols stubbed, NumPy SAT "

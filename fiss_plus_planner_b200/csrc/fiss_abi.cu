@@ -653,7 +653,13 @@ int32_t launch_grid(fiss_handle* h, cudaStream_t st, const fiss::GridArgs& a, si
   kl.block = dim3((unsigned)threads);
   kl.smem = smem;
   kl.pdl = a.chained != 0;
-  kl.push(a);
+  fiss::GridArgs b = a;
+  if (h->record == nullptr) {  // nothing can fail between here and the launch but the launch itself
+    b.seq_prev = h->lattice_seq;
+    if (++h->lattice_seq == 0) ++h->lattice_seq;  // (0 is "not numbered")
+    b.seq = h->lattice_seq;
+  }
+  kl.push(b);
   return issue(h, st, kl);
 }
 
@@ -770,17 +776,21 @@ int32_t eval_grid(fiss_handle* h, cudaStream_t st, const double* d_ego, int B, c
     a.n_big = 0;
     a.items = base_items * a.n_chunks;
   }
-  a.seq = ++h->lattice_seq;
+  // Directly issued launches are numbered (the number is taken when the launch is issued: launch_grid) and publish their
+  // number when all their CTAs are done; a launch recorded for a graph carries no number, publishes nothing and draws from
+  // a counter pair of its own -- its arguments then stay the same from call to call (no node to patch), and it never runs
+  // beside another launch (a graph launch and the kernels around it serialise).
+  a.seq = 0;
   h->lattice_chained = a.chained ? (yaw ? 2 : 1) : 0;
   a.shadow = nullptr;
   a.shadow_stride = (a.slots * a.d_chunk * a.nv + 1) & ~1;
   if (a.chained) {  // shadow blocks for the first items' cost / flags: one per resident CTA, two sets
     const size_t set_bytes = (size_t)h->sm_count * 8 * a.shadow_stride * 20;  // (<= 8 resident CTAs per SM)
     FISS_CUDA(h, h->d_shadow.ensure(2 * set_bytes));
-    a.shadow = h->d_shadow.as<unsigned char>() + (size_t)(a.seq & 1u) * set_bytes;
+    a.shadow = h->d_shadow.as<unsigned char>() + (size_t)((h->lattice_seq + 1) & 1u) * set_bytes;
   }
-  h->work_parity ^= 1;
-  a.work = h->d_work.as<uint32_t>() + 2 * h->work_parity;  // (allocated and zeroed by fiss_create)
+  if (h->record == nullptr) h->work_parity ^= 1;
+  a.work = h->d_work.as<uint32_t>() + (h->record == nullptr ? 2 * h->work_parity : 6);  // (allocated and zeroed by fiss_create)
   a.work_done = h->d_work.as<uint32_t>() + 4;
   const int warps = std::max(1, std::min(fiss::grid_warps(yaw), a.slots * std::max(g->nv + a.d_chunk, a.d_chunk * g->nv)));
   if (L.bytes > kSmemLimit)

@@ -128,7 +128,7 @@ struct GridArgs {
   // the SMs that the previous launch's last items leave idle.  Inputs are read-only; before a CTA's first OUTPUT write the
   // earlier launches must be out of the way:
   //   materialised rows  the previous lattice launch may still be writing the same buffer: wait until its last CTA has
-  //                      published `seq - 1` in work[4] (every lattice launch publishes its sequence number when all its CTAs
+  //                      published `seq_prev` in work[4] (every lattice launch publishes its sequence number when all its CTAs
   //                      are done -- it is running or finished by the time a CTA of this launch exists, so the wait ends);
   //   cost / flags       the previous step's record kernel reads them: griddepcontrol.wait (the whole previous kernel) --
   //                      but not before the CTA's SECOND item: the first item's values go to a shadow block of the engine
@@ -137,7 +137,8 @@ struct GridArgs {
   int32_t chained;
   unsigned char* shadow;   // [gridDim.x][shadow_stride * 20 B]
   int32_t shadow_stride;   // entries per CTA (>= candidates of an item)
-  uint32_t seq;        // sequence number of this lattice launch on its handle
+  uint32_t seq;        // sequence number of this lattice launch among the directly issued ones of its handle (0: part of a graph)
+  uint32_t seq_prev;   // ... and the number of the directly issued launch before it (0: none)
   uint32_t* work;      // [0] next item to hand out (minus gridDim.x), [1] CTAs that are done (both zero between launches;
                        // two such pairs alternate between launches: [0..1], [2..3]); [4] sequence number of the last
                        // lattice launch all of whose CTAs are done (work_done points at it)
@@ -357,6 +358,7 @@ __global__ void __launch_bounds__(grid_warps(kYaw) * 32, grid_min_ctas(kYaw)) fi
   uint32_t* rows_done = npairs + 2;  // longitudinal rows of the item that have folded their frame points into the boxes
   uint32_t* row_task = npairs + 3;   // next row task of stage A
   uint32_t* next_item = npairs + 4;  // [2] the CTA's next work item, by item parity (fetched one item ahead)
+  uint32_t* n_shadow = npairs + 6;   // [2] entries in the CTA's shadow block, by item parity (chained launches)
   uint32_t* pairs = reinterpret_cast<uint32_t*>(smem_raw + L.pairs);      // (row << 16 | checked step) with any proximity bit
   uint32_t* cflags = reinterpret_cast<uint32_t*>(smem_raw + L.cflags);    // per candidate: collision / curvature bits
   uint32_t* masks = reinterpret_cast<uint32_t*>(smem_raw + L.masks);
@@ -490,19 +492,19 @@ __global__ void __launch_bounds__(grid_warps(kYaw) * 32, grid_min_ctas(kYaw)) fi
   __syncthreads();
   FISS_PHASE(0);
 
-  bool chain_waited = false, mat_gate_open = false;
-  // shadow block of this CTA (chained launches): ids, costs, flags; the thread that wrote an entry copies it into the volume
-  int n_shadow = -1;  // entries in the shadow block (-1: the first item is still to come)
-  auto flush_shadow = [&]() {
+  // Chained launches keep no state in registers across items (the kernel is register-bound): a CTA's first item is item
+  // blockIdx.x, and the number of entries in its shadow block sits in shared memory.
+  if (threadIdx.x == 0) n_shadow[0] = 0u;
+  // shadow block of this CTA: ids, costs, flags; the thread that wrote an entry copies it into the volume
+  auto flush_shadow = [&](uint32_t n) {
     int64_t* sh_id = reinterpret_cast<int64_t*>(a.shadow + (size_t)blockIdx.x * a.shadow_stride * 20);
     double* sh_cost = reinterpret_cast<double*>(sh_id + a.shadow_stride);
     uint32_t* sh_flags = reinterpret_cast<uint32_t*>(sh_cost + a.shadow_stride);
-    for (int cidx = threadIdx.x; cidx < n_shadow; cidx += blockDim.x) {
+    for (uint32_t cidx = threadIdx.x; cidx < n; cidx += blockDim.x) {
       const int64_t id = sh_id[cidx];
       a.cost[id] = sh_cost[cidx];
       a.flags[id] = sh_flags[cidx];
     }
-    n_shadow = 0;
   };
   int par = 0;
   for (uint32_t item = blockIdx.x; item < n_items; item = next_item[par ^ 1], par ^= 1) {
@@ -842,13 +844,12 @@ __global__ void __launch_bounds__(grid_warps(kYaw) * 32, grid_min_ctas(kYaw)) fi
     if (kYaw) {
       // first output write of this CTA (materialised rows): the previous launch -- which may still be writing the same
       // buffers, or reading this launch's cost / flags volume -- has to be over
-      if (a.chained && !mat_gate_open) {
-        mat_gate_open = true;
+      if (a.chained && item == blockIdx.x) {  // (the CTA's first item; later ones are behind this wait anyway)
         if (lane == 0) {
           uint32_t done;
           do {
             asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(done) : "l"(a.work_done) : "memory");
-          } while ((int32_t)(done - (a.seq - 1u)) < 0);
+          } while ((int32_t)(done - a.seq_prev) < 0);
         }
         __syncwarp();
       }
@@ -913,11 +914,10 @@ __global__ void __launch_bounds__(grid_warps(kYaw) * 32, grid_min_ctas(kYaw)) fi
 
     // chained launches: the first item's cost / flags go to the CTA's shadow block; from the second item on the volume is
     // written directly, behind the wait for the previous kernel of the stream
-    const bool to_shadow = a.chained && !chain_waited && n_shadow < 0;
-    if (a.chained && !chain_waited && !to_shadow) {
-      pdl_wait_producer();
-      chain_waited = true;
-      flush_shadow();
+    const bool to_shadow = a.chained && item == blockIdx.x;
+    if (a.chained && !to_shadow) {
+      pdl_wait_producer();  // (returns at once from the CTA's third item on)
+      flush_shadow(n_shadow[par]);
     }
     // ---- stage C: one lane per candidate -- cost (cost_function.py:41-50) and the flags word; then the reset of the
     // per-item state and the fetch of the next item's slots
@@ -953,7 +953,7 @@ __global__ void __launch_bounds__(grid_warps(kYaw) * 32, grid_min_ctas(kYaw)) fi
           a.flags[out_id] = flags_v;
         }
       }
-      if (to_shadow) n_shadow = n_cand;
+      if (threadIdx.x == 0) n_shadow[par ^ 1] = to_shadow ? (uint32_t)n_cand : 0u;  // (read by the next item's stage C)
       reset_item_state();
     }
     FISS_STAMP(10);
@@ -961,9 +961,10 @@ __global__ void __launch_bounds__(grid_warps(kYaw) * 32, grid_min_ctas(kYaw)) fi
     ++trace_item;
 #endif
   }
-  if (a.chained && !chain_waited) {  // (a CTA with a single item)
+  if (a.chained) {  // (a CTA with a single item still has its shadow block to copy)
+    __syncthreads();  // n_shadow[] of the last item is thread 0's
     pdl_wait_producer();
-    flush_shadow();
+    flush_shadow(n_shadow[par]);
   }
   // Every CTA has drawn its last (out-of-range) item by now and its output writes are issued: the last one to leave zeroes
   // the counters for the launch after the next and publishes this launch's sequence number (chained launches, above).
@@ -974,7 +975,7 @@ __global__ void __launch_bounds__(grid_warps(kYaw) * 32, grid_min_ctas(kYaw)) fi
       a.work[0] = 0u;
       a.work[1] = 0u;
       __threadfence();
-      asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(a.work_done), "r"(a.seq) : "memory");
+      if (a.seq) asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(a.work_done), "r"(a.seq) : "memory");
     }
   }
 #ifdef FISS_PHASE_TIMING
