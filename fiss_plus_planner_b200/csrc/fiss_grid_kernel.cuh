@@ -32,6 +32,10 @@
 //   stage C  one lane per candidate: cost = (lon + lat terms)/n, flags word; reset of the per-item state, fetch of
 //            the next item's ego states
 //
+// Work items are dealt with a grid stride or drawn through a device counter (big items first, single pairs last), and a
+// launch can be CHAINED to the previous kernel of its stream -- scheduled as that kernel's CTAs retire, waiting for it only
+// before its first output writes (GridArgs::dynamic, ::chained; fiss_abi.cu eval_grid says when).
+//
 // so a candidate costs ~2 table reads per step instead of two polynomial solves, a 7-step segment
 // search and an M x n/2 obstacle sweep.  All arithmetic is FP64 with the same expressions as the
 // generic kernel in fiss_kernels.cuh (masks, n' and winners are bit-identical between the two).
