@@ -848,6 +848,7 @@ __global__ void __launch_bounds__(grid_warps(kYaw) * 32, grid_min_ctas(kYaw)) fi
     if (kYaw) {
       // first output write of this CTA (materialised rows): the previous launch -- which may still be writing the same
       // buffers, or reading this launch's cost / flags volume -- has to be over
+#ifndef FISS_TEST_NO_GATE  // (negative control of tests/test_gpu_chained.py: built without the guard, the tests must fail)
       if (a.chained && item == blockIdx.x) {  // (the CTA's first item; later ones are behind this wait anyway)
         if (lane == 0) {
           uint32_t done;
@@ -857,6 +858,7 @@ __global__ void __launch_bounds__(grid_warps(kYaw) * 32, grid_min_ctas(kYaw)) fi
         }
         __syncwarp();
       }
+#endif
       const int ns = a.n_stride;
       const uint32_t ns_magic = a.ns_magic;  // f / ns for f < 2^20 / ns
       const int n_blocks = (n_lon * ns + 30) / 31;
@@ -918,9 +920,15 @@ __global__ void __launch_bounds__(grid_warps(kYaw) * 32, grid_min_ctas(kYaw)) fi
 
     // chained launches: the first item's cost / flags go to the CTA's shadow block; from the second item on the volume is
     // written directly, behind the wait for the previous kernel of the stream
+#ifdef FISS_TEST_NO_SHADOW  // (negative control: the first item's cost / flags straight into the volume, no wait at all)
+    const bool to_shadow = false;
+#else
     const bool to_shadow = a.chained && item == blockIdx.x;
+#endif
     if (a.chained && !to_shadow) {
+#if !defined(FISS_TEST_NO_WAIT) && !defined(FISS_TEST_NO_SHADOW)  // (negative control, as above)
       pdl_wait_producer();  // (returns at once from the CTA's third item on)
+#endif
       flush_shadow(n_shadow[par]);
     }
     // ---- stage C: one lane per candidate -- cost (cost_function.py:41-50) and the flags word; then the reset of the
