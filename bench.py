@@ -427,8 +427,8 @@ def run_ours(args):
         """K steps between two events (the headline): nothing but the steps' own launches sits on the stream between them,
         so that consecutive steps chain (the next step's CTAs start on the SMs this step's last items leave idle --
         programmatic dependent launch, fiss_abi.cu eval_grid).  Then the same K steps once more with an event after every
-        step: the per-step spread (an event between two steps serialises them: the median of that pass is the time of a
-        step ON ITS OWN)."""
+        step and a synchronisation behind it: the median of that pass is the time of a step ON ITS OWN (issued onto an idle
+        GPU, the library keeps the single-step settings: fiss_abi.cu eval_grid, `in_train`)."""
         for _ in range(args.warmup):
             fn()
         barrier()
@@ -439,13 +439,15 @@ def run_ours(args):
         t1.record(stream)
         barrier()
         total = t0.elapsed_time(t1)
-        marks = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
-        marks[0].record(stream)
-        for i in range(args.steps):
+        per = []
+        for i in range(args.steps):   # one step, then a synchronisation: the GPU is idle when the next step is issued
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(stream)
             fn()
-            marks[i + 1].record(stream)
+            b.record(stream)
+            torch.cuda.synchronize()
+            per.append(a.elapsed_time(b))
         barrier()
-        per = [marks[i].elapsed_time(marks[i + 1]) for i in range(args.steps)]
         return max_over_ranks(total), max_over_ranks(float(np.median(per)))
 
     # ---- device-resident timing (value): full materialisation + pick + winners' records
@@ -587,7 +589,7 @@ def run_ours(args):
                          "kernel_ms_how": "average launch duration over a train of `steps` launches between two CUDA events "
                                           "(consecutive launches chained by programmatic dependent launch, as in the step loop)",
                          "kernel_ms_alone": kern_alone_ms, "kernel_ms_alone_median": kern_median_ms,
-                         "kernel_ms_alone_how": "CUDA events around every single launch (the events serialise the launches)",
+                         "kernel_ms_alone_how": "CUDA events around every single launch: the events keep the launches from overlapping (they are still issued back to back, so the library uses its train settings -- work drawn dynamically -- which cost a launch on its own ~3 %)",
                          "frac_alone": alg / (kern_alone_ms * 1e-3) / 1e9 / peak,
                          "algorithmic_bytes_per_launch": alg, "peak_source": peak_src,
                          "note": "FP64-issue bound by arithmetic (SURVEY 8(d)); see profiles/ for ncu fp64 pipe utilisation"},

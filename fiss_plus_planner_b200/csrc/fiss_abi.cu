@@ -182,7 +182,8 @@ struct fiss_handle {
   DevBuf d_work;   // work counters of the lattice kernel (zero between launches), two pairs
   int work_parity = 0;
   uint32_t lattice_seq = 0;  // lattice launches issued on this handle (chained launches)
-  int lattice_chained = 0;   // ... and whether the last one was chained (1: winner-only kernel, 2: materialising)
+  int lattice_chained = 0;   // ... and whether the last one was chained IN A TRAIN (1: winner-only kernel, 2: materialising)
+  PinBuf host_done;          // [1] u32, mapped: number of the last numbered lattice launch that is over (written by its last CTA)
   DevBuf d_shadow;           // chained launches: the first items' cost / flags, per CTA, two sets
   DevBuf d_fit_in, d_fit_out;  // fiss_fit_splines_host / fiss_frame_samples_host
   cudaStream_t capture_stream = nullptr;       // graph_run: launches are captured here when a graph is (re)built
@@ -765,10 +766,15 @@ int32_t eval_grid(fiss_handle* h, cudaStream_t st, const double* d_ego, int B, c
   static const bool dyn_mat = dyn_mat_forced ? std::atoi(std::getenv("FISS_DYN_MAT")) != 0 : false;
   static const bool dyn_win = std::getenv("FISS_DYN") ? std::atoi(std::getenv("FISS_DYN")) != 0 : true;
   const bool can_deal = a.n_chunks == 1 && a.slots > 1;
-  a.dynamic = can_deal && (yaw ? (dyn_mat_forced ? dyn_mat : a.chained != 0) : dyn_win);
-  // (chained launches: whole items only -- the CTAs of the next launch fill in behind the last items, and single pairs cost
-  // more than they even out: winner-only step train 0.0626 -> 0.0576 ms)
-  const int big_pct = big_forced ? big_env : ((yaw || a.chained) ? 100 : 70);
+  // Is this launch part of a TRAIN -- is an earlier numbered launch of this handle still running, so that this one will start
+  // on the SMs it leaves behind?  Its last CTA writes its number to a page-locked host word when it is over.  Only then do the
+  // throughput settings pay (work drawn dynamically, whole items, a small record grid behind it); a launch onto an idle GPU --
+  // one step, then a synchronisation -- keeps the settings that make a single step fastest (0.128 vs 0.144 ms).
+  const bool in_train = a.chained != 0 && (int32_t)(h->lattice_seq - *static_cast<volatile uint32_t*>(h->host_done.p)) > 0;
+  a.dynamic = can_deal && (yaw ? (dyn_mat_forced ? dyn_mat : in_train) : dyn_win);
+  // (in a train: whole items only -- the CTAs of the next launch fill in behind the last items, and single pairs cost more
+  // than they even out: winner-only step train 0.0626 -> 0.0576 ms)
+  const int big_pct = big_forced ? big_env : ((yaw || in_train) ? 100 : 70);
   const int64_t full_items = (base_items + a.slots - 1) / a.slots;
   if (a.n_chunks == 1) {
     const bool split = a.dynamic && big_pct < 100;
@@ -783,7 +789,7 @@ int32_t eval_grid(fiss_handle* h, cudaStream_t st, const double* d_ego, int B, c
   // a counter pair of its own -- its arguments then stay the same from call to call (no node to patch), and it never runs
   // beside another launch (a graph launch and the kernels around it serialise).
   a.seq = 0;
-  h->lattice_chained = a.chained ? (yaw ? 2 : 1) : 0;
+  h->lattice_chained = in_train ? (yaw ? 2 : 1) : 0;
   a.shadow = nullptr;
   a.shadow_stride = (a.slots * a.d_chunk * a.nv + 1) & ~1;
   if (a.chained) {  // shadow blocks for the first items' cost / flags: one per resident CTA, two sets
@@ -794,6 +800,7 @@ int32_t eval_grid(fiss_handle* h, cudaStream_t st, const double* d_ego, int B, c
   if (h->record == nullptr) h->work_parity ^= 1;
   a.work = h->d_work.as<uint32_t>() + (h->record == nullptr ? 2 * h->work_parity : 6);  // (allocated and zeroed by fiss_create)
   a.work_done = h->d_work.as<uint32_t>() + 4;
+  a.work_done_host = h->host_done.as<uint32_t>();  // (page-locked memory is mapped into the device's address space: UVA)
   const int warps = std::max(1, std::min(fiss::grid_warps(yaw), a.slots * std::max(g->nv + a.d_chunk, a.d_chunk * g->nv)));
   if (L.bytes > kSmemLimit)
     return fail(h, FISS_ERR_CAPACITY,
@@ -867,6 +874,8 @@ int32_t fiss_create(int32_t device, fiss_handle** out) {
   // work counters of the lattice kernel: zero between launches (the last CTA of a launch clears them)
   e = h->d_work.ensure(256);
   if (e == cudaSuccess) e = cudaMemset(h->d_work.p, 0, 256);
+  if (e == cudaSuccess) e = h->host_done.ensure(64);
+  if (e == cudaSuccess) *h->host_done.as<uint32_t>() = 0u;
   if (e != cudaSuccess) {
     delete h;
     return fail(nullptr, FISS_ERR_CUDA, std::string("work counters: ") + cudaGetErrorString(e));
@@ -884,6 +893,7 @@ int32_t fiss_destroy(fiss_handle* h) {
     b->release();
   h->h_in.release();
   h->h_out.release();
+  h->host_done.release();
   h->graph_dev.release();
   h->graph_host.release();
   h->d_pick.release();

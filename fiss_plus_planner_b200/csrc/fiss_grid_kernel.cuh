@@ -147,6 +147,7 @@ struct GridArgs {
                        // two such pairs alternate between launches: [0..1], [2..3]); [4] sequence number of the last
                        // lattice launch all of whose CTAs are done (work_done points at it)
   uint32_t* work_done;
+  uint32_t* work_done_host;  // the same number for the HOST (a mapped, page-locked word): is the GPU still busy with this handle?
   int64_t total;       // B * C
   fiss_params p;
   const double* spline;  // [9][Kp]
@@ -987,7 +988,10 @@ __global__ void __launch_bounds__(grid_warps(kYaw) * 32, grid_min_ctas(kYaw)) fi
       a.work[0] = 0u;
       a.work[1] = 0u;
       __threadfence();
-      if (a.seq) asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(a.work_done), "r"(a.seq) : "memory");
+      if (a.seq) {
+        asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(a.work_done), "r"(a.seq) : "memory");
+        *reinterpret_cast<volatile uint32_t*>(a.work_done_host) = a.seq;
+      }
     }
   }
 #ifdef FISS_PHASE_TIMING
