@@ -397,11 +397,12 @@ int32_t launch_record(fiss_handle* h, cudaStream_t st, const fiss::EvalArgs& a, 
   // there until it is over, and the next step's lattice kernel cannot be scheduled before every record CTA is resident: a
   // small record grid (it loops over the problems) leaves the retiring slots to the next step sooner.  Nobody waits for this
   // kernel but the next step's second items and the next record kernel.  (FISS_REC_CTAS overrides.)
-  // Measured on the B200 (cfg4 step trains): 32 CTAs behind the materialising kernel (0.125 -> 0.108 ms per step; 128: 0.121),
-  // 64 behind the winner-only kernel (0.068 -> 0.058; 32: 0.065, 128: 0.060).
+  // Measured on the B200 (cfg4 step trains): 32 CTAs behind the materialising kernel (0.125 -> 0.108 ms per step; 24: 0.112,
+  // 48: 0.110, 64: 0.115, 128: 0.120); behind the winner-only kernel a record CTA fits the slot of one retiring lattice CTA and
+  // the full grid is best (0.068 -> 0.056; 64: 0.058, 32: 0.066).
   static const int rec_cap = std::getenv("FISS_REC_CTAS") ? std::max(1, std::atoi(std::getenv("FISS_REC_CTAS"))) : 0;
-  if (a.after_producer && h->record == nullptr && h->lattice_chained)
-    ctas = std::min<int64_t>(ctas, rec_cap > 0 ? rec_cap : (h->lattice_chained == 2 ? 32 : 64));
+  if (a.after_producer && h->record == nullptr && h->lattice_chained && (rec_cap > 0 || h->lattice_chained == 2))
+    ctas = std::min<int64_t>(ctas, rec_cap > 0 ? rec_cap : 32);
   kl.grid = dim3((unsigned)std::max<int64_t>(1, ctas));
   kl.block = dim3((unsigned)(fiss::kRecWarps * 32));
   kl.smem = smem;
