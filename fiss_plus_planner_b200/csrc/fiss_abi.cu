@@ -132,7 +132,7 @@ struct StepGraph {
 
 // One in-flight call of the streaming entry points (fiss_plan_grid_submit / _wait): its own device buffers, pinned
 // bounce buffers and events, so that the copy-back of one lane runs under the kernels of the other.
-constexpr int kLanes = 2;
+constexpr int kLanes = FISS_LANES;
 struct Lane {
   DevBuf d_ego, d_cost, d_flags, d_win, d_records;
   PinBuf h_in, h_out;
@@ -1505,7 +1505,7 @@ int32_t fiss_plan_grid_submit(fiss_handle* h, void* stream, int32_t lane, const 
                               const fiss_params* p, int32_t* best_idx, double* best_cost, int32_t* best_meta,
                               double* records, int32_t n_stride) {
   if (!h) return FISS_ERR_INVALID;
-  if (lane < 0 || lane >= kLanes) return fail(h, FISS_ERR_INVALID, "plan_grid_submit: lane must be 0 or 1");
+  if (lane < 0 || lane >= kLanes) return fail(h, FISS_ERR_INVALID, "plan_grid_submit: lane must be 0 .. FISS_LANES - 1");
   if (!ego || !best_idx || !best_cost || B < 1) return fail(h, FISS_ERR_INVALID, "plan_grid_submit: bad arguments");
   Lane& ln = h->lanes[lane];
   if (ln.pending) return fail(h, FISS_ERR_STATE, "plan_grid_submit: the lane still has a call in flight (fiss_plan_grid_wait it first)");
@@ -1581,7 +1581,7 @@ int32_t fiss_plan_grid_submit(fiss_handle* h, void* stream, int32_t lane, const 
 
 int32_t fiss_plan_grid_wait(fiss_handle* h, int32_t lane) {
   if (!h) return FISS_ERR_INVALID;
-  if (lane < 0 || lane >= kLanes) return fail(h, FISS_ERR_INVALID, "plan_grid_wait: lane must be 0 or 1");
+  if (lane < 0 || lane >= kLanes) return fail(h, FISS_ERR_INVALID, "plan_grid_wait: lane must be 0 .. FISS_LANES - 1");
   Lane& ln = h->lanes[lane];
   if (!ln.pending) return fail(h, FISS_ERR_STATE, "plan_grid_wait: nothing in flight on this lane");
   FISS_ON_DEVICE(h);

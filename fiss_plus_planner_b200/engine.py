@@ -314,9 +314,9 @@ class FissEngine:
         return out
 
     def plan_grid_submit(self, lane: int, ego: np.ndarray, grid: LatticeGrid, params: FissParams, out: dict, stream=None):
-        """Streaming ``plan_grid``: enqueue batch ``ego [B, 6]`` on ``lane`` (0 / 1) and return at once; the results land
+        """Streaming ``plan_grid``: enqueue batch ``ego [B, 6]`` on ``lane`` (0 .. 3) and return at once; the results land
         in ``out`` (from ``alloc_plan_outputs(..., want_volume=False)``) when ``plan_grid_wait(lane)`` returns.  The
-        copy-back of one lane overlaps the kernels of the other."""
+        copy-back of one lane overlaps the kernels of the others."""
         assert isinstance(ego, np.ndarray) and ego.ndim == 2 and ego.dtype == np.float64 and ego.flags.c_contiguous
         p = self._out_ptrs(out)
         self._check(self._lib.fiss_plan_grid_submit(

@@ -207,11 +207,13 @@ int32_t fiss_plan_grid_host(fiss_handle* h, void* stream, const double* ego, int
                             double* records, int32_t n_stride, double* cost, uint32_t* flags);
 
 /* Streaming twin of fiss_plan_grid_host for a sequence of batches (planning.py:120-128 calls plan() once per step; a
- * batched caller submits one batch of ego states per step): `submit` enqueues H2D + kernels + D2H of batch k on lane
- * k % 2 and returns; `wait` blocks until that lane's winners / records are in the caller's buffers.  The device->host
- * copy of one lane runs on a second stream under the kernels of the other lane.  Buffers as in fiss_plan_grid_host
- * (no cost / flags volume); they must stay valid until the lane has been waited for.  A lane with a call in flight
- * refuses another submit (FISS_ERR_STATE). */
+ * batched caller submits one batch of ego states per step): `submit` enqueues H2D + kernels + D2H of a batch on one of
+ * FISS_LANES lanes and returns; `wait` blocks until that lane's winners / records are in the caller's buffers.  The
+ * device->host copy of one lane runs on a second stream under the kernels of the others: two lanes in rotation hide the
+ * copy-back (a third measured no faster on a B200: the step is bound by what the kernels' stream carries).  Buffers as in
+ * fiss_plan_grid_host (no cost / flags volume); they must stay valid until the lane has been waited for.  A lane with a call
+ * in flight refuses another submit (FISS_ERR_STATE). */
+#define FISS_LANES 4
 int32_t fiss_plan_grid_submit(fiss_handle* h, void* stream, int32_t lane, const double* ego, int32_t B, const fiss_grid* g,
                               const fiss_params* p, int32_t* best_idx, double* best_cost, int32_t* best_meta,
                               double* records, int32_t n_stride);

@@ -138,4 +138,4 @@ def test_submit_wait_streams_batches():
     with pytest.raises(FissError):
         eng.plan_grid_wait(1)
     with pytest.raises(FissError):
-        eng.plan_grid_submit(2, batches[0], grid, prm, out)
+        eng.plan_grid_submit(4, batches[0], grid, prm, out)   # lanes 0 .. FISS_LANES - 1 = 3
