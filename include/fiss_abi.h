@@ -184,9 +184,14 @@ int32_t fiss_full_records_dev(fiss_handle* h, void* stream, const double* d_ego6
                               double* d_records, double* d_cost, uint32_t* d_flags, int32_t n_stride);
 
 /* One plan step on caller-owned DEVICE buffers: fiss_eval_grid_dev + fiss_pick_winners_dev (the pick fused into the
- * record launch when d_records != NULL) as ONE call -- and, from the second call with the same buffers on, as one
- * cudaGraphLaunch of an instantiated graph whose kernel nodes are patched when the parameters change (time_step_now
- * moves every cycle, planning.py:124-128).  Asynchronous on `stream`.  d_mat / d_records / d_best_meta may be NULL. */
+ * record launch when d_records != NULL) as ONE call.  A small batch (launch-latency bound) runs, from the second call with
+ * the same buffers on, as one cudaGraphLaunch of an instantiated graph whose kernel nodes are patched when the parameters
+ * change (time_step_now moves every cycle, planning.py:124-128).  A batch that fills the GPU (B * nt >= 2 * SMs) is issued
+ * launch by launch and CHAINED to the previous kernel of `stream` (programmatic dependent launch): called back to back, the
+ * next step's CTAs start on the SMs this step's last work items leave idle and wait for the earlier launches only before
+ * they write (so consecutive calls may share every buffer); an event record, a copy or a foreign kernel between two calls
+ * simply ends a chain.  Not meant to be stream-captured into a caller's own graph with chaining on (FISS_CHAIN=0 then).
+ * Asynchronous on `stream`; use a handle from one stream at a time.  d_mat / d_records / d_best_meta may be NULL. */
 int32_t fiss_plan_grid_dev(fiss_handle* h, void* stream, const double* d_ego, int32_t B, const fiss_grid* g,
                            const fiss_params* p, double* d_cost, uint32_t* d_flags, double* d_mat, int32_t* d_best_idx,
                            double* d_best_cost, int32_t* d_best_meta, double* d_records, int32_t n_stride);
