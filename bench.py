@@ -591,7 +591,7 @@ def run_ours(args):
                          "kernel_ms_how": "average launch duration over a train of `steps` launches between two CUDA events "
                                           "(consecutive launches chained by programmatic dependent launch, as in the step loop)",
                          "kernel_ms_alone": kern_alone_ms, "kernel_ms_alone_median": kern_median_ms,
-                         "kernel_ms_alone_how": "CUDA events around every single launch: the events keep the launches from overlapping (they are still issued back to back, so the library uses its train settings -- work drawn dynamically -- which cost a launch on its own ~3 %)",
+                         "kernel_ms_alone_how": "CUDA events around every single launch: the events keep the launches from overlapping (they are still issued back to back, so the library uses its train settings -- work drawn dynamically -- which cost a launch on its own ~3 %: with the single-step settings it measures 0.116-0.118 ms, profiles/r2y_chain_ab.txt)",
                          "frac_alone": alg / (kern_alone_ms * 1e-3) / 1e9 / peak,
                          "algorithmic_bytes_per_launch": alg, "peak_source": peak_src,
                          "note": "FP64-issue bound by arithmetic (SURVEY 8(d)); see profiles/ for ncu fp64 pipe utilisation"},
