@@ -662,7 +662,10 @@ int32_t launch_grid(fiss_handle* h, cudaStream_t st, const fiss::GridArgs& a, si
     b.seq = h->lattice_seq;
   }
   kl.push(b);
-  return issue(h, st, kl);
+  const int32_t rc = issue(h, st, kl);
+  // a launch that was never issued publishes nothing: its number must not become anybody's predecessor
+  if (rc != FISS_OK && b.seq != 0) h->lattice_seq = b.seq_prev;
+  return rc;
 }
 
 int32_t eval_grid(fiss_handle* h, cudaStream_t st, const double* d_ego, int B, const fiss_grid* g, int n_max,
